@@ -1,0 +1,116 @@
+"""ctypes binding of the C ABI in include/gespmm.h (lib/libgespmm.so).
+
+This is the binding a non-PyTorch host would write; it carries no torch types.  Device
+pointers are plain integers (e.g. ``tensor.data_ptr()``), streams are ``cudaStream_t`` as
+integers (0 / None = legacy default stream, which the reference launches on:
+pytorch-custom/spmm_kernel.cu:189,196,203).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+OK = 0
+ERR_INVALID_ARG, ERR_CUDA, ERR_TOO_LARGE, ERR_IO, ERR_WORKSPACE, ERR_NOMEM = -1, -2, -3, -4, -5, -6
+LONG_ROW = 4096
+
+# every symbol include/gespmm.h declares
+SYMBOLS = (
+    "gespmm_version", "gespmm_error_string", "gespmm_csr_spmm_f32", "gespmm_csr_spmm_f32_host",
+    "gespmm_csr2csc_workspace_bytes", "gespmm_csr2csc_f32", "gespmm_read_mtx", "gespmm_free_host",
+)
+
+_lib = None
+
+
+class GespmmError(RuntimeError):
+    def __init__(self, code, what):
+        self.code = code
+        super().__init__("%s failed: %s (code %d)" % (what, error_string(code), code))
+
+
+def lib():
+    """Load lib/libgespmm.so; there is no fallback if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_build.LIB):
+            raise ImportError(
+                "%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(this package has no CPU or pure-PyTorch path)" % _build.LIB)
+        L = ctypes.CDLL(_build.LIB)
+        i64, p, sz = ctypes.c_int64, ctypes.c_void_p, ctypes.c_size_t
+        L.gespmm_version.restype = ctypes.c_int
+        L.gespmm_error_string.restype = ctypes.c_char_p
+        L.gespmm_error_string.argtypes = [ctypes.c_int]
+        L.gespmm_csr_spmm_f32.restype = ctypes.c_int
+        L.gespmm_csr_spmm_f32.argtypes = [i64, i64, i64, i64, p, p, p, p, i64, p, i64, p]
+        L.gespmm_csr_spmm_f32_host.restype = ctypes.c_int
+        L.gespmm_csr_spmm_f32_host.argtypes = [i64, i64, i64, i64, p, p, p, p, i64, p, i64, ctypes.c_int]
+        L.gespmm_csr2csc_workspace_bytes.restype = sz
+        L.gespmm_csr2csc_workspace_bytes.argtypes = [i64, i64, i64]
+        L.gespmm_csr2csc_f32.restype = ctypes.c_int
+        L.gespmm_csr2csc_f32.argtypes = [i64, i64, i64, p, p, p, p, p, p, p, sz, p]
+        L.gespmm_read_mtx.restype = ctypes.c_int
+        L.gespmm_read_mtx.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                      ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(p), ctypes.POINTER(p),
+                                      ctypes.POINTER(p)]
+        L.gespmm_free_host.restype = None
+        L.gespmm_free_host.argtypes = [p]
+        _lib = L
+    return _lib
+
+
+def version():
+    return lib().gespmm_version()
+
+
+def error_string(code):
+    return lib().gespmm_error_string(int(code)).decode()
+
+
+def csr_spmm_f32(M, N, K, nnz, rowptr, colind, val, B, ldb, C, ldc, stream=None):
+    """Raw call with device pointers (ints).  ``val`` may be None/0 (all-ones A)."""
+    rc = lib().gespmm_csr_spmm_f32(M, N, K, nnz, rowptr, colind, val or None, B, ldb, C, ldc, stream or None)
+    if rc != OK:
+        raise GespmmError(rc, "gespmm_csr_spmm_f32")
+
+
+def csr_spmm_host(rowptr, colind, val, B, device=0):
+    """Host numpy arrays in, host numpy C out, through gespmm_csr_spmm_f32_host."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+    colind = np.ascontiguousarray(colind, dtype=np.int32)
+    B = np.ascontiguousarray(B, dtype=np.float32)
+    if val is not None:
+        val = np.ascontiguousarray(val, dtype=np.float32)
+    M, (N, K), nnz = rowptr.shape[0] - 1, B.shape, colind.shape[0]
+    C = np.empty((M, K), dtype=np.float32)
+    rc = lib().gespmm_csr_spmm_f32_host(M, N, K, nnz, rowptr.ctypes.data, colind.ctypes.data,
+                                        val.ctypes.data if val is not None else None, B.ctypes.data, K,
+                                        C.ctypes.data, K, device)
+    if rc != OK:
+        raise GespmmError(rc, "gespmm_csr_spmm_f32_host")
+    return C
+
+
+def read_mtx(path):
+    """MatrixMarket file -> (nrows, ncols, rowptr, colind, val) as numpy arrays (readMtx post-conditions)."""
+    L = lib()
+    nr, nc, nnz = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()
+    rp, ci, vv = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    rc = L.gespmm_read_mtx(os.fsencode(path), ctypes.byref(nr), ctypes.byref(nc), ctypes.byref(nnz),
+                           ctypes.byref(rp), ctypes.byref(ci), ctypes.byref(vv))
+    if rc != OK:
+        raise GespmmError(rc, "gespmm_read_mtx(%s)" % path)
+    try:
+        n = nnz.value
+        rowptr = np.ctypeslib.as_array(ctypes.cast(rp, ctypes.POINTER(ctypes.c_int32)), (nr.value + 1,)).copy()
+        if n:
+            colind = np.ctypeslib.as_array(ctypes.cast(ci, ctypes.POINTER(ctypes.c_int32)), (n,)).copy()
+            val = np.ctypeslib.as_array(ctypes.cast(vv, ctypes.POINTER(ctypes.c_float)), (n,)).copy()
+        else:
+            colind, val = np.empty(0, np.int32), np.empty(0, np.float32)
+    finally:
+        L.gespmm_free_host(rp); L.gespmm_free_host(ci); L.gespmm_free_host(vv)
+    return nr.value, nc.value, rowptr, colind, val

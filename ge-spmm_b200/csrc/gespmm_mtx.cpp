@@ -1,0 +1,189 @@
+// gespmm_mtx.cpp -- MatrixMarket coordinate file -> host CSR (gespmm_read_mtx, include/gespmm.h).
+//
+// Same post-conditions as the reference's readMtx<float> followed by the CLI's COO->CSR
+// (util/util.hpp:286-333, 218-284, 75-102; util/mmio.hpp:215-336; spmm_test.cu:557-581), a
+// different construction: the file is slurped once and tokenised by hand (the reference calls
+// fscanf three times per entry), entries are bucketed by row with a counting sort and each
+// row is then ordered by column (the reference sorts a vector of 4-tuples, O(nnz log nnz)),
+// and the CSR arrays are produced directly.
+//
+//   general    keep every entry, duplicates and self-loops included        (util.hpp:327)
+//   symmetric  mirror off-diagonal entries, then drop self-loops and repeated (row,col)
+//              (util.hpp:226-261)
+//   pattern    values are 1 (util.hpp:177); integer / real are parsed as such (util.hpp:113-116)
+//   complex    no entries are read (util.hpp:315-320 has no branch for it)
+//   skew-symmetric / hermitian are accepted by the banner parser and treated as general
+//              (readMtx only tests mm_is_symmetric, util.hpp:323)
+#include <algorithm>
+#include <cctype>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gespmm.h"
+
+namespace {
+
+struct Entry { int32_t col; float val; };
+
+inline const char *skip_ws(const char *p, const char *end) {
+    while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r' || *p == '\v' || *p == '\f')) ++p;
+    return p;
+}
+
+// %d semantics: optional sign, decimal digits; stops at the first other character.
+inline bool parse_int(const char *&p, const char *end, long long &out) {
+    p = skip_ws(p, end);
+    if (p >= end) return false;
+    bool neg = false;
+    if (*p == '-' || *p == '+') { neg = (*p == '-'); ++p; }
+    if (p >= end || *p < '0' || *p > '9') return false;
+    long long v = 0;
+    while (p < end && *p >= '0' && *p <= '9') { v = v * 10 + (*p - '0'); ++p; }
+    out = neg ? -v : v;
+    return true;
+}
+
+inline bool parse_float(const char *&p, const char *end, float &out) {
+    p = skip_ws(p, end);
+    if (p >= end) return false;
+    char *q = nullptr;
+    out = strtof(p, &q);  // buffer is NUL-terminated
+    if (q == p) return false;
+    p = q;
+    return true;
+}
+
+std::string lower(std::string s) {
+    for (auto &c : s) c = (char)tolower((unsigned char)c);
+    return s;
+}
+
+template <typename T>
+T *dup_to_malloc(const std::vector<T> &v) {
+    T *p = (T *)malloc((v.empty() ? 1 : v.size()) * sizeof(T));
+    if (p && !v.empty()) memcpy(p, v.data(), v.size() * sizeof(T));
+    return p;
+}
+
+}  // namespace
+
+extern "C" int gespmm_read_mtx(const char *path, int32_t *nrows, int32_t *ncols, int64_t *nnz_out,
+                               int32_t **rowptr_out, int32_t **colind_out, float **val_out)
+{
+    if (!path || !nrows || !ncols || !nnz_out || !rowptr_out || !colind_out || !val_out) return GESPMM_ERR_INVALID_ARG;
+    *rowptr_out = nullptr; *colind_out = nullptr; *val_out = nullptr;
+    FILE *f = fopen(path, "rb");
+    if (!f) return GESPMM_ERR_IO;
+    std::vector<char> buf;
+    {
+        fseek(f, 0, SEEK_END);
+        long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        if (sz < 0) { fclose(f); return GESPMM_ERR_IO; }
+        buf.resize((size_t)sz + 1);
+        size_t got = fread(buf.data(), 1, (size_t)sz, f);
+        fclose(f);
+        buf[got] = '\0';
+        buf.resize(got + 1);
+    }
+    const char *p = buf.data(), *end = buf.data() + buf.size() - 1;
+
+    // banner line: five tokens, the first is matched by prefix, the rest case-insensitively
+    const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
+    std::string line(p, eol ? eol : end);
+    char t0[65] = {0}, t1[65] = {0}, t2[65] = {0}, t3[65] = {0}, t4[65] = {0};
+    if (sscanf(line.c_str(), "%64s %64s %64s %64s %64s", t0, t1, t2, t3, t4) != 5) return GESPMM_ERR_IO;
+    if (strncmp(t0, "%%MatrixMarket", 14) != 0) return GESPMM_ERR_IO;
+    const std::string object = lower(t1), format = lower(t2), field = lower(t3), symm = lower(t4);
+    if (object != "matrix" || format != "coordinate") return GESPMM_ERR_IO;
+    const bool is_int = field == "integer", is_real = field == "real", is_pat = field == "pattern";
+    if (!is_int && !is_real && !is_pat && field != "complex") return GESPMM_ERR_IO;
+    const bool is_sym = symm == "symmetric";
+    if (!is_sym && symm != "general" && symm != "hermitian" && symm != "skew-symmetric") return GESPMM_ERR_IO;
+    p = eol ? eol + 1 : end;
+
+    // comment lines, then the size line (blank lines before it are tolerated like mmio does)
+    long long M = 0, N = 0, nz = 0;
+    while (true) {
+        if (p >= end) return GESPMM_ERR_IO;
+        eol = (const char *)memchr(p, '\n', (size_t)(end - p));
+        const char *le = eol ? eol : end;
+        if (*p == '%') { p = eol ? eol + 1 : end; continue; }
+        const char *q = p;
+        if (parse_int(q, le, M) && parse_int(q, le, N) && parse_int(q, le, nz)) { p = eol ? eol + 1 : end; break; }
+        p = eol ? eol + 1 : end;
+    }
+    if (M < 0 || N < 0 || nz < 0 || M > INT32_MAX - 1 || N > INT32_MAX || nz > INT32_MAX) return GESPMM_ERR_TOO_LARGE;
+
+    std::vector<int32_t> er, ec;
+    std::vector<float> ev;
+    er.reserve((size_t)nz); ec.reserve((size_t)nz); ev.reserve((size_t)nz);
+    if (is_int || is_real || is_pat) {
+        for (long long i = 0; i < nz; i++) {
+            long long r, c;
+            if (!parse_int(p, end, r)) break;  // fewer entries than promised: keep what was read
+            if (!parse_int(p, end, c)) c = 0;
+            float v = 1.0f;
+            if (is_int) { long long iv = 0; if (parse_int(p, end, iv)) v = (float)(int)iv; }
+            else if (is_real) { if (!parse_float(p, end, v)) v = 0.0f; }
+            er.push_back((int32_t)(r - 1)); ec.push_back((int32_t)(c - 1)); ev.push_back(v);
+        }
+    }
+    size_t n = er.size();
+    for (size_t i = 0; i < n; i++)
+        if (er[i] < 0 || er[i] >= M || ec[i] < 0 || ec[i] >= N) return GESPMM_ERR_IO;
+    if (is_sym) {
+        if (M != N) return GESPMM_ERR_IO;
+        for (size_t i = 0; i < n; i++)
+            if (er[i] != ec[i]) { er.push_back(ec[i]); ec.push_back(er[i]); ev.push_back(ev[i]); }
+        n = er.size();
+    }
+    if (n > (size_t)INT32_MAX) return GESPMM_ERR_TOO_LARGE;
+
+    // bucket by row (stable), order each row by column (stable)
+    std::vector<int32_t> rowptr((size_t)M + 1, 0);
+    for (size_t i = 0; i < n; i++) rowptr[(size_t)er[i] + 1]++;
+    for (long long r = 0; r < M; r++) rowptr[r + 1] += rowptr[r];
+    std::vector<Entry> ent(n);
+    {
+        std::vector<int32_t> cursor(rowptr.begin(), rowptr.end() - 1);
+        for (size_t i = 0; i < n; i++) ent[(size_t)cursor[er[i]]++] = Entry{ec[i], ev[i]};
+    }
+    std::vector<int32_t>().swap(er); std::vector<int32_t>().swap(ec); std::vector<float>().swap(ev);
+    for (long long r = 0; r < M; r++) {
+        Entry *b = ent.data() + rowptr[r], *e = ent.data() + rowptr[r + 1];
+        if (e - b > 1 && !std::is_sorted(b, e, [](const Entry &x, const Entry &y) { return x.col < y.col; }))
+            std::stable_sort(b, e, [](const Entry &x, const Entry &y) { return x.col < y.col; });
+    }
+
+    std::vector<int32_t> colind;
+    std::vector<float> val;
+    colind.reserve(n); val.reserve(n);
+    if (is_sym) {
+        std::vector<int32_t> newptr((size_t)M + 1, 0);
+        for (long long r = 0; r < M; r++) {
+            int32_t last = -1;
+            for (int32_t q = rowptr[r]; q < rowptr[r + 1]; q++) {
+                const int32_t c = ent[q].col;
+                if (c == (int32_t)r || c == last) continue;  // self-loop / repeated (row,col)
+                colind.push_back(c); val.push_back(ent[q].val);
+                last = c;
+            }
+            newptr[r + 1] = (int32_t)colind.size();
+        }
+        rowptr.swap(newptr);
+    } else {
+        for (size_t i = 0; i < n; i++) { colind.push_back(ent[i].col); val.push_back(ent[i].val); }
+    }
+
+    int32_t *rp = dup_to_malloc(rowptr);
+    int32_t *ci = dup_to_malloc(colind);
+    float *vv = dup_to_malloc(val);
+    if (!rp || !ci || !vv) { free(rp); free(ci); free(vv); return GESPMM_ERR_NOMEM; }
+    *nrows = (int32_t)M; *ncols = (int32_t)N; *nnz_out = (int64_t)colind.size();
+    *rowptr_out = rp; *colind_out = ci; *val_out = vv;
+    return GESPMM_OK;
+}

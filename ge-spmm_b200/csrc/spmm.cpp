@@ -1,0 +1,104 @@
+// spmm.cpp -- PyTorch extension module `spmm`, the operator surface of the reference
+// (pytorch-custom/spmm.cpp:96-101): csr_spmm, csr_spmm_no_edge_value, csr2csc with the same
+// names, arity and argument meaning.  Thin shim over the C ABI in include/gespmm.h.
+//
+// Differences from the reference shim, all deliberate:
+//   * argument predicates (CUDA device, contiguous, int32 / float32) are the reference's
+//     (spmm.cpp:30-41, 50-58, 77-91) but raise a Python exception (TORCH_CHECK) instead of a
+//     C assert() that aborts the process; shapes are checked too;
+//   * launches go to the current PyTorch stream under a device guard (the reference uses the
+//     legacy default stream and no guard: spmm_kernel.cu:189,196,203);
+//   * csr2csc works (the reference's uses an uninitialised cuSPARSE handle: spmm_kernel.cu:386).
+// There is no CPU path: CPU tensors are rejected.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include "gespmm.h"
+
+namespace {
+
+void check_index(const torch::Tensor &t, const char *name)
+{
+    TORCH_CHECK(t.device().type() == torch::kCUDA, name, " must be a CUDA tensor (this build has no CPU path)");
+    TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
+    TORCH_CHECK(t.dtype() == torch::kInt32, name, " must be int32");
+    TORCH_CHECK(t.dim() == 1, name, " must be 1-D");
+}
+
+void check_float(const torch::Tensor &t, const char *name, int dim)
+{
+    TORCH_CHECK(t.device().type() == torch::kCUDA, name, " must be a CUDA tensor (this build has no CPU path)");
+    TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
+    TORCH_CHECK(t.dtype() == torch::kFloat32, name, " must be float32");
+    TORCH_CHECK(t.dim() == dim, name, " must be ", dim, "-D");
+}
+
+torch::Tensor run(const torch::Tensor &rowptr, const torch::Tensor &colind, const float *val, const torch::Tensor &B)
+{
+    TORCH_CHECK(rowptr.size(0) >= 1, "A_rowptr must have at least one element");
+    TORCH_CHECK(rowptr.device() == B.device() && colind.device() == B.device(), "all tensors must be on B's device");
+    const int64_t M = rowptr.size(0) - 1, N = B.size(0), K = B.size(1), nnz = colind.size(0);
+    c10::cuda::CUDAGuard guard(B.device());
+    auto out = torch::empty({M, K}, B.options());  // spmm_kernel.cu:182-184
+    cudaStream_t stream = at::cuda::getCurrentCUDAStream();
+    const int rc = gespmm_csr_spmm_f32(M, N, K, nnz, rowptr.data_ptr<int>(), colind.data_ptr<int>(), val,
+                                       B.data_ptr<float>(), K, out.data_ptr<float>(), K, stream);
+    TORCH_CHECK(rc == GESPMM_OK, "gespmm_csr_spmm_f32 failed: ", gespmm_error_string(rc));
+    return out;
+}
+
+}  // namespace
+
+// pytorch-custom/spmm.cpp:24-43
+torch::Tensor csr_spmm(torch::Tensor A_rowptr, torch::Tensor A_colind, torch::Tensor A_csrVal, torch::Tensor B)
+{
+    check_index(A_rowptr, "A_rowptr");
+    check_index(A_colind, "A_colind");
+    check_float(A_csrVal, "A_csrVal", 1);
+    check_float(B, "B", 2);
+    TORCH_CHECK(A_csrVal.size(0) == A_colind.size(0), "A_csrVal and A_colind must have the same length");
+    TORCH_CHECK(A_csrVal.device() == B.device(), "all tensors must be on B's device");
+    return run(A_rowptr, A_colind, A_csrVal.data_ptr<float>(), B);
+}
+
+// pytorch-custom/spmm.cpp:45-60
+torch::Tensor csr_spmm_no_edge_value(torch::Tensor A_rowptr, torch::Tensor A_colind, torch::Tensor B)
+{
+    check_index(A_rowptr, "A_rowptr");
+    check_index(A_colind, "A_colind");
+    check_float(B, "B", 2);
+    return run(A_rowptr, A_colind, nullptr, B);
+}
+
+// pytorch-custom/spmm.cpp:70-93: fills colptr / rowind in place, returns the CSC values.
+torch::Tensor csr2csc(torch::Tensor rowptr, torch::Tensor colind, torch::Tensor colptr, torch::Tensor rowind,
+                      torch::Tensor csr_data)
+{
+    check_index(rowptr, "rowptr");
+    check_index(colind, "colind");
+    check_index(colptr, "colptr");
+    check_index(rowind, "rowind");
+    check_float(csr_data, "csr_data", 1);
+    const int64_t M = rowptr.size(0) - 1, N = colptr.size(0) - 1, nnz = colind.size(0);
+    TORCH_CHECK(M >= 0 && N >= 0, "rowptr and colptr must be non-empty");
+    TORCH_CHECK(rowind.size(0) == nnz && csr_data.size(0) == nnz, "rowind / csr_data must have nnz elements");
+    c10::cuda::CUDAGuard guard(rowptr.device());
+    auto csc_val = torch::empty({nnz}, csr_data.options());  // spmm_kernel.cu:471-473
+    const size_t ws_bytes = gespmm_csr2csc_workspace_bytes(M, N, nnz);
+    auto ws = torch::empty({(int64_t)ws_bytes}, rowptr.options().dtype(torch::kUInt8));
+    cudaStream_t stream = at::cuda::getCurrentCUDAStream();
+    const int rc = gespmm_csr2csc_f32(M, N, nnz, rowptr.data_ptr<int>(), colind.data_ptr<int>(),
+                                      csr_data.data_ptr<float>(), colptr.data_ptr<int>(), rowind.data_ptr<int>(),
+                                      csc_val.data_ptr<float>(), ws.data_ptr(), ws_bytes, stream);
+    TORCH_CHECK(rc == GESPMM_OK, "gespmm_csr2csc_f32 failed: ", gespmm_error_string(rc));
+    return csc_val;
+}
+
+PYBIND11_MODULE(spmm, m)
+{
+    m.doc() = "spmm in CSR format. csr_spmm is the kernel with edge value. csr2csc provides the format transformation";
+    m.def("csr_spmm", &csr_spmm, "CSR SPMM");
+    m.def("csr_spmm_no_edge_value", &csr_spmm_no_edge_value, "CSR SPMM NO EDGE VALUE");
+    m.def("csr2csc", &csr2csc, "csr2csc");
+}

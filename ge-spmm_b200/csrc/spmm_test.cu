@@ -1,0 +1,262 @@
+// spmm_test -- benchmark CLI over .mtx input; the B200 build's counterpart of the reference
+// driver (spmm_test.cu:495-826, run by run_test.sh:9,22).
+//
+//   ./spmm_test <file.mtx> [device_id] [options]
+//
+// Same contract as the reference: read the matrix (readMtx post-conditions), build CSR with
+// every value forced to 1 (spmm_test.cu:573-574), fill B[N x max_ncols] with
+// (rand()%100-50)/100 (:592-594), halve max_ncols until the device allocations fit
+// (:619-635), then for K = 128, 256, ... <= max_ncols time ITER back-to-back launches with
+// CUDA events (:726-762) and append "<baseline GFLOP/s>,<ours GFLOP/s>," to
+// ./spmm_test_out.out (row label and newline come from the calling script, run_test.sh:8-10).
+// B is one buffer re-interpreted as [N x K] row-major for each K (:592-594, 756).
+//
+// Differences, all deliberate:
+//   * The first cell of each pair was cuSPARSE csrmm2 (:730-738), which no longer exists and
+//     which this build must not use.  It is now the reference's own kernel (spmm_test2<float>,
+//     tile_row 8) when --baseline-lib points at a library exporting ref_spmm_time_ms (built by
+//     oracle/Makefile from the reference sources); otherwise the cell is 0.
+//   * --seed replaces srand(time(0)) (:586-588); --validate replaces #define VALIDATE (:19).
+//   * Errors return a non-zero exit status instead of falling through.
+//   * --json prints one JSON object per K with the byte model and roofline fraction.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "gespmm.h"
+
+#define CHECK_CUDA(call)                                                                         \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            fprintf(stderr, "Cuda runtime error in line %d of file %s : %s \n", __LINE__, __FILE__, \
+                    cudaGetErrorString(e_));                                                     \
+            return 1;                                                                            \
+        }                                                                                        \
+    } while (0)
+
+typedef float (*ref_time_fn)(int, int, int, int, int *, int *, float *, float *, float *, int, int);
+typedef int (*ref_run_fn)(int, int, int, int, int *, int *, float *, float *, float *);
+
+static void usage(const char *argv0)
+{
+    fprintf(stderr,
+            "usage: %s <file.mtx> [device_id] [--K a,b,c] [--iters n] [--seed s] [--valued] [--validate]\n"
+            "          [--baseline-lib libref_cli_kernels.so] [--json] [--out file] [--hbm-gbs peak]\n",
+            argv0);
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 2) { usage(argv[0]); return 2; }
+    const char *mtx = argv[1];
+    int dev = 0, iters = 200, max_ncols = 512;
+    unsigned seed = 1;
+    bool validate = false, json = false, valued_kernel = true;  // the reference CLI times the valued kernel with A == 1
+    bool unvalued = false;
+    double hbm_gbs = 8000.0;
+    std::string out_path = "spmm_test_out.out", baseline_lib;
+    std::vector<int> ks;
+    int argi = 2;
+    if (argi < argc && argv[argi][0] != '-') dev = atoi(argv[argi++]);
+    for (; argi < argc; argi++) {
+        std::string a = argv[argi];
+        auto need = [&](const char *name) -> const char * {
+            if (argi + 1 >= argc) { fprintf(stderr, "%s needs a value\n", name); exit(2); }
+            return argv[++argi];
+        };
+        if (a == "--K") {
+            std::string s = need("--K");
+            size_t pos = 0;
+            while (pos < s.size()) {
+                size_t q = s.find(',', pos);
+                if (q == std::string::npos) q = s.size();
+                ks.push_back(atoi(s.substr(pos, q - pos).c_str()));
+                pos = q + 1;
+            }
+        } else if (a == "--iters") iters = atoi(need("--iters"));
+        else if (a == "--seed") seed = (unsigned)strtoul(need("--seed"), nullptr, 10);
+        else if (a == "--validate") validate = true;
+        else if (a == "--json") json = true;
+        else if (a == "--unvalued") unvalued = true;
+        else if (a == "--valued") valued_kernel = true;
+        else if (a == "--baseline-lib") baseline_lib = need("--baseline-lib");
+        else if (a == "--out") out_path = need("--out");
+        else if (a == "--hbm-gbs") hbm_gbs = atof(need("--hbm-gbs"));
+        else { usage(argv[0]); return 2; }
+    }
+    if (unvalued) valued_kernel = false;
+    for (int k : ks) {
+        if (k <= 0) { fprintf(stderr, "bad --K\n"); return 2; }
+        if (k > max_ncols) max_ncols = k;
+    }
+    if (iters <= 0) iters = 1;
+
+    FILE *fpo = fopen(out_path.c_str(), "a");
+    if (!fpo) { fprintf(stderr, "cannot open %s\n", out_path.c_str()); return 1; }
+
+    printf("reading file ...\n");
+    int32_t M = 0, N = 0;
+    int64_t nnz = 0;
+    int32_t *rowptr = nullptr, *colind = nullptr;
+    float *aval = nullptr;
+    int rc = gespmm_read_mtx(mtx, &M, &N, &nnz, &rowptr, &colind, &aval);
+    if (rc != GESPMM_OK) {
+        if (rc == GESPMM_ERR_IO) printf("File %s not found or not a MatrixMarket coordinate file", mtx);
+        fprintf(stderr, "gespmm_read_mtx: %s\n", gespmm_error_string(rc));
+        fclose(fpo);
+        return 1;
+    }
+    for (int64_t i = 0; i < nnz; i++) aval[i] = 1.0f;  // spmm_test.cu:574
+    printf("read file ok. N=%d nnz=%lld\n", M, (long long)nnz);
+
+    // dense operand, same recipe as the reference (glibc rand)
+    float *B = (float *)malloc((size_t)max_ncols * (size_t)N * sizeof(float));
+    if (!B) { fprintf(stderr, "Host malloc failed\n"); fclose(fpo); return 1; }
+    srand(seed);
+    for (size_t i = 0; i < (size_t)max_ncols * (size_t)N; i++) B[i] = float(rand() % 100 - 50) / 100;
+
+    if (cudaSetDevice(dev) != cudaSuccess) {
+        fprintf(stderr, "no usable CUDA device %d: this build has no CPU path\n", dev);
+        fclose(fpo);
+        return 1;
+    }
+    int32_t *d_rowptr = nullptr, *d_colind = nullptr;
+    float *d_val = nullptr, *d_B = nullptr, *d_C = nullptr;
+    while (true) {  // spmm_test.cu:619-635
+        cudaError_t s1 = cudaMalloc(&d_rowptr, (size_t)(M + 1) * 4);
+        cudaError_t s2 = cudaMalloc(&d_colind, (size_t)(nnz > 0 ? nnz : 1) * 4);
+        cudaError_t s3 = cudaMalloc(&d_val, (size_t)(nnz > 0 ? nnz : 1) * 4);
+        cudaError_t s4 = cudaMalloc(&d_B, (size_t)max_ncols * (size_t)(N > 0 ? N : 1) * 4);
+        cudaError_t s5 = cudaMalloc(&d_C, (size_t)max_ncols * (size_t)(M > 0 ? M : 1) * 4);
+        if (s1 == cudaSuccess && s2 == cudaSuccess && s3 == cudaSuccess && s4 == cudaSuccess && s5 == cudaSuccess) break;
+        cudaGetLastError();
+        cudaFree(d_rowptr); cudaFree(d_colind); cudaFree(d_val); cudaFree(d_B); cudaFree(d_C);
+        d_rowptr = d_colind = nullptr; d_val = d_B = d_C = nullptr;
+        max_ncols /= 2;
+        if (max_ncols == 0) { fprintf(stderr, "device allocation failed\n"); fclose(fpo); return 1; }
+    }
+    printf("max_ncols = %d\n", max_ncols);
+    CHECK_CUDA(cudaMemcpy(d_rowptr, rowptr, (size_t)(M + 1) * 4, cudaMemcpyHostToDevice));
+    CHECK_CUDA(cudaMemcpy(d_colind, colind, (size_t)nnz * 4, cudaMemcpyHostToDevice));
+    CHECK_CUDA(cudaMemcpy(d_val, aval, (size_t)nnz * 4, cudaMemcpyHostToDevice));
+    CHECK_CUDA(cudaMemcpy(d_B, B, (size_t)max_ncols * (size_t)N * 4, cudaMemcpyHostToDevice));
+
+    ref_time_fn ref_time = nullptr;
+    ref_run_fn ref_run = nullptr;
+    if (!baseline_lib.empty()) {
+        void *h = dlopen(baseline_lib.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if (!h) { fprintf(stderr, "cannot load %s: %s\n", baseline_lib.c_str(), dlerror()); fclose(fpo); return 1; }
+        ref_time = (ref_time_fn)dlsym(h, "ref_spmm_time_ms");
+        ref_run = (ref_run_fn)dlsym(h, "ref_spmm_wrapper");
+        if (!ref_time || !ref_run) { fprintf(stderr, "%s lacks ref_spmm_time_ms/ref_spmm_wrapper\n", baseline_lib.c_str()); fclose(fpo); return 1; }
+    }
+
+    if (ks.empty())
+        for (int k = 128; k <= max_ncols; k *= 2) ks.push_back(k);  // spmm_test.cu:726
+
+    cudaEvent_t start, stop;
+    CHECK_CUDA(cudaEventCreate(&start));
+    CHECK_CUDA(cudaEventCreate(&stop));
+    const float *d_val_arg = valued_kernel ? d_val : nullptr;
+    int status = 0;
+
+    if (validate) {
+        // CPU golden of the reference's VALIDATE block (spmm_test.cu:595-605), K = max_ncols;
+        // a checker, never a compute path.  Tolerance 1e-2 absolute as in the reference (:676,694)
+        // is far too loose to mean anything; report the maximum difference and fail above 1e-4
+        // relative to sum|a||b|.
+        const int K = ks.back() <= max_ncols ? ks.back() : max_ncols;
+        std::vector<float> golden((size_t)M * K), C((size_t)M * K);
+        std::vector<float> mag((size_t)M * K);
+        for (int i = 0; i < M; i++)
+            for (int k = 0; k < K; k++) {
+                float acc = 0.f, m = 0.f;
+                for (int p = rowptr[i]; p < rowptr[i + 1]; p++) {
+                    acc += aval[p] * B[(size_t)K * colind[p] + k];
+                    m += fabsf(B[(size_t)K * colind[p] + k]);
+                }
+                golden[(size_t)i * K + k] = acc;
+                mag[(size_t)i * K + k] = m;
+            }
+        CHECK_CUDA(cudaMemset(d_C, 0xff, (size_t)M * K * 4));
+        rc = gespmm_csr_spmm_f32(M, N, K, nnz, d_rowptr, d_colind, d_val_arg, d_B, K, d_C, K, nullptr);
+        if (rc != GESPMM_OK) { fprintf(stderr, "gespmm_csr_spmm_f32: %s\n", gespmm_error_string(rc)); return 1; }
+        CHECK_CUDA(cudaMemcpy(C.data(), d_C, (size_t)M * K * 4, cudaMemcpyDeviceToHost));
+        double worst = 0.0;
+        size_t bad = 0;
+        for (size_t i = 0; i < C.size(); i++) {
+            const double d = fabs((double)C[i] - (double)golden[i]);
+            const double tol = 1e-4 * fmax(fabs((double)golden[i]), (double)mag[i]) + 1e-30;
+            if (!(d <= tol)) {
+                if (bad == 0) printf("gespmm WA: C[%zu, %zu] = %g, golden = %g\n", i / K, i % K, C[i], golden[i]);
+                bad++;
+            }
+            if (d > worst) worst = d;
+        }
+        printf("validate K=%d: max |diff| = %.3g, mismatches = %zu\n", K, worst, bad);
+        if (bad) status = 3;
+        if (ref_run) {
+            std::vector<float> R((size_t)M * K);
+            CHECK_CUDA(cudaMemset(d_C, 0xff, (size_t)M * K * 4));
+            ref_run(2, 8, M, K, d_rowptr, d_colind, d_val, d_B, d_C);
+            CHECK_CUDA(cudaDeviceSynchronize());
+            CHECK_CUDA(cudaMemcpy(R.data(), d_C, (size_t)M * K * 4, cudaMemcpyDeviceToHost));
+            size_t diff_bits = 0;
+            for (size_t i = 0; i < C.size(); i++) diff_bits += memcmp(&C[i], &R[i], 4) != 0;
+            printf("validate K=%d: elements differing bitwise from the reference kernel = %zu\n", K, diff_bits);
+        }
+    }
+
+    printf("running tests...\n");
+    for (int K : ks) {
+        if (K > max_ncols) continue;
+        const double gflop = (double)nnz * 2 / 1000000 * K;  // per launch, in MFLOP/ms == GFLOP/s units below
+        float rt = 0.f;
+        double base_gflops = 0.0;
+        if (ref_time) {
+            const float ms = ref_time(2, 8, M, K, d_rowptr, d_colind, d_val, d_B, d_C, 3, iters);
+            if (ms > 0) base_gflops = gflop / ms;
+        }
+        fprintf(fpo, "%f,", base_gflops);
+
+        for (int i = 0; i < 3; i++)
+            rc = gespmm_csr_spmm_f32(M, N, K, nnz, d_rowptr, d_colind, d_val_arg, d_B, K, d_C, K, nullptr);
+        if (rc != GESPMM_OK) { fprintf(stderr, "gespmm_csr_spmm_f32: %s\n", gespmm_error_string(rc)); return 1; }
+        CHECK_CUDA(cudaEventRecord(start, 0));
+        for (int i = 0; i < iters; i++)
+            gespmm_csr_spmm_f32(M, N, K, nnz, d_rowptr, d_colind, d_val_arg, d_B, K, d_C, K, nullptr);
+        CHECK_CUDA(cudaEventRecord(stop, 0));
+        CHECK_CUDA(cudaEventSynchronize(stop));
+        CHECK_CUDA(cudaEventElapsedTime(&rt, start, stop));
+        CHECK_CUDA(cudaGetLastError());
+        const double ms = rt / iters;
+        const double ours = gflop / ms;
+        fprintf(fpo, "%f,", ours);
+        const double bytes_min = 4.0 * (M + 1) + 4.0 * nnz + (valued_kernel ? 4.0 * nnz : 0.0) + 4.0 * (double)N * K + 4.0 * (double)M * K;
+        const double gbs = bytes_min / ms / 1e6;
+        if (json)
+            printf("{\"mtx\": \"%s\", \"M\": %d, \"N\": %d, \"nnz\": %lld, \"K\": %d, \"valued\": %s, \"iters\": %d, "
+                   "\"ms\": %.6f, \"gflops\": %.3f, \"ref_kernel_gflops\": %.3f, \"bytes_min\": %.0f, "
+                   "\"achieved_gbs\": %.2f, \"hbm_peak_gbs\": %.1f, \"roofline_frac\": %.4f}\n",
+                   mtx, M, N, (long long)nnz, K, valued_kernel ? "true" : "false", iters, ms, ours, base_gflops,
+                   bytes_min, gbs, hbm_gbs, gbs / hbm_gbs);
+        else
+            printf("K=%d: %.3f ms, %.1f GFLOP/s (reference kernel %.1f), %.1f GB/s of bytes_min\n", K, ms, ours,
+                   base_gflops, gbs);
+    }
+
+    cudaEventDestroy(start); cudaEventDestroy(stop);
+    cudaFree(d_rowptr); cudaFree(d_colind); cudaFree(d_val); cudaFree(d_B); cudaFree(d_C);
+    gespmm_free_host(rowptr); gespmm_free_host(colind); gespmm_free_host(aval);
+    free(B);
+    fclose(fpo);
+    return status;
+}

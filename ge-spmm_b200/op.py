@@ -1,0 +1,140 @@
+"""SPMMFunction and GCNConv: mirror of the reference's pytorch-custom/op.py.
+
+Same names, signatures and argument meaning as op.py:8-36 (SPMMFunction) and op.py:77-152
+(GCNConv); the SpMM itself is the sm_100a kernel behind ``spmm.csr_spmm`` /
+``spmm.csr_spmm_no_edge_value`` (csrc/spmm.cpp -> include/gespmm.h).
+
+Differences, all deliberate:
+  * the extension is prebuilt in-tree (``build.py``) instead of JIT-compiled at import
+    (op.py:6); if it is missing it is built once with ``make``; if that fails the import
+    fails -- there is no fallback implementation;
+  * ``glorot`` / ``zeros`` are restated here (op.py:75 imports them from torch_geometric,
+    which this image does not have);
+  * forward does not stash ``feat`` in ctx (op.py:16 keeps [N,K] alive for nothing);
+  * ``normalize=False`` works (op.py:131-134 calls ``rowptr.shape(0)``, a TypeError);
+  * the "[I] Treat edge weight as no_grad." notice (op.py:31) is printed once, not per call.
+"""
+import importlib
+import math
+import os
+import sys
+
+import torch
+from torch.nn import Parameter
+
+from . import build as _build
+
+
+def _load_spmm():
+    if not os.path.exists(_build.EXT):
+        _build.build()
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("spmm", _build.EXT)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sys.modules.setdefault("gespmm_b200.spmm", mod)
+    return mod
+
+
+spmm = _load_spmm()
+
+_warned_no_grad = False
+
+
+class SPMMFunction(torch.autograd.Function):
+    """out = A @ feat with A given as CSR (forward) and CSC (backward: A^T @ grad_out)."""
+
+    @staticmethod
+    def forward(ctx, rowptr, colind, colptr, rowind, feat, edge_weight_csr=None, edge_weight_csc=None):
+        if edge_weight_csr is None:
+            out = spmm.csr_spmm_no_edge_value(rowptr, colind, feat)
+        else:
+            out = spmm.csr_spmm(rowptr, colind, edge_weight_csr, feat)
+        ctx.backward_csc = (colptr, rowind, edge_weight_csr, edge_weight_csc)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        global _warned_no_grad
+        colptr, rowind, edge_weight_csr, edge_weight_csc = ctx.backward_csc
+        grad_out = grad_out.contiguous()
+        if edge_weight_csr is not None:
+            if edge_weight_csc is None:
+                raise RuntimeError(
+                    "Backward of SPMM require edge values in both src-first and dst-first order, "
+                    "and do not support gradients for edge values. Call with SPMMFunction.apply(rowptr, colind, "
+                    "colptr, rowind, in_feat, edge_value_row_first, edge_value_col_first")
+            grad_feat = spmm.csr_spmm(colptr, rowind, edge_weight_csc, grad_out)
+            if not _warned_no_grad:
+                print("[I] Treat edge weight as no_grad.")
+                _warned_no_grad = True
+        else:
+            grad_feat = spmm.csr_spmm_no_edge_value(colptr, rowind, grad_out)
+        return None, None, None, None, grad_feat, None, None
+
+
+def glorot(tensor):
+    """torch_geometric.nn.inits.glorot: U(-a, a), a = sqrt(6 / (fan_in + fan_out))."""
+    if tensor is not None:
+        stdv = math.sqrt(6.0 / (tensor.size(-2) + tensor.size(-1)))
+        tensor.data.uniform_(-stdv, stdv)
+
+
+def zeros(tensor):
+    if tensor is not None:
+        tensor.data.fill_(0)
+
+
+class GCNConv(torch.nn.Module):
+    """x' = D_in^-1/2 A D_out^-1/2 (x W) + b, aggregation through SPMMFunction (op.py:77-152)."""
+
+    def __init__(self, in_channels, out_channels, improved=False, cached=False, bias=True, normalize=True, **kwargs):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.improved = improved
+        self.cached = cached
+        self.normalize = normalize
+        self.weight = Parameter(torch.empty(in_channels, out_channels))
+        if bias:
+            self.bias = Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        glorot(self.weight)
+        zeros(self.bias)
+        self.cached_result = None
+        self.cached_num_edges = None
+
+    @staticmethod
+    def in_deg_sqrt(indptr):
+        return (1 / torch.sqrt((indptr[1:] - indptr[:-1]).float())).unsqueeze(dim=1)
+
+    @staticmethod
+    def out_deg_sqrt(indptr):
+        return (1 / torch.sqrt((indptr[1:] - indptr[:-1]).float())).unsqueeze(dim=1)
+
+    def forward(self, x, rowptr, colind, colptr, rowind, edge_weight_csr=None, edge_weight_csc=None):
+        x = torch.matmul(x, self.weight)
+        if not self.cached or self.cached_result is None:
+            if self.normalize:
+                in_deg_norm = self.in_deg_sqrt(rowptr)
+                out_deg_norm = self.out_deg_sqrt(colptr)
+            else:
+                in_deg_norm = torch.ones(rowptr.shape[0] - 1, 1, dtype=x.dtype, device=x.device)
+                out_deg_norm = torch.ones(colptr.shape[0] - 1, 1, dtype=x.dtype, device=x.device)
+            self.cached_result = in_deg_norm, out_deg_norm
+        in_deg_norm, out_deg_norm = self.cached_result
+        if self.normalize:
+            x = x * out_deg_norm
+        aggr_out = SPMMFunction.apply(rowptr, colind, colptr, rowind, x, edge_weight_csr, edge_weight_csc)
+        if self.normalize:
+            aggr_out = aggr_out * in_deg_norm
+        if self.bias is not None:
+            aggr_out = aggr_out + self.bias
+        return aggr_out
+
+    def __repr__(self):
+        return "{}({}, {})".format(self.__class__.__name__, self.in_channels, self.out_channels)

@@ -1,0 +1,118 @@
+/*
+ * gespmm.h -- C ABI of the B200-native CSR x dense SpMM (libgespmm.so).
+ *
+ * This is the drop-in boundary for the one hot path of hgyhungry/ge-spmm:
+ *     C[M,K] = A_csr[M,N] * B[N,K]      fp32 data, int32 CSR indices, row-major dense.
+ * Every reference call site of that path passes the same raw-pointer tuple
+ * (m, k, rowptr, colind, [val], B, C); the entry points below are what an FFI binding
+ * for it would bind.  Plain pointers and sizes only -- no torch, no C++ types.
+ *
+ *   entry point                    replaces (reference file:line)
+ *   -----------------------------  ---------------------------------------------------
+ *   gespmm_csr_spmm_f32            spmm_cuda / spmm_cuda_no_edge_value launch blocks
+ *                                  (pytorch-custom/spmm_kernel.cu:425-458, 175-207) and the
+ *                                  kernels they pick (topoSimple/topoCache/topoCacheCoarsen
+ *                                  SPMMKernel :31-173, spmm_test0/1/2 :210-379);
+ *                                  spmmWrapper (spmm_test.cu:456-492) and spmm_test0..4<T>
+ *                                  (spmm_test.cu:64-454);  XTopoCsrmm<float>
+ *                                  (dgl-custom/binary_reduce_sum.cu:309-335) has the same shape.
+ *   gespmm_csr2csc_f32             csr2cscKernel / csr2csc_cuda
+ *                                  (pytorch-custom/spmm_kernel.cu:381-423, 460-477)
+ *   gespmm_read_mtx / _free        readMtx<float> + COO->CSR of the CLI
+ *                                  (util/util.hpp:286-333, spmm_test.cu:557-581)
+ *
+ * Conventions
+ *   - All device pointers must live on the device that is current when the call is made.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, which is what
+ *     the reference launches on: spmm_kernel.cu:189,196,203).  Calls are asynchronous on it.
+ *   - No allocation and no hidden state inside gespmm_csr_spmm_f32: re-entrant, graph-capturable.
+ *   - Return value: GESPMM_OK or a negative GESPMM_ERR_* code.  Never exits the process
+ *     (the reference's checkCudaError macros call exit(): spmm_kernel.cu:5-19).
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     GESPMM_ERR_CUDA.
+ */
+#ifndef GESPMM_H
+#define GESPMM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GESPMM_OK                0
+#define GESPMM_ERR_INVALID_ARG  -1   /* null pointer with non-zero size, negative size, ld < K   */
+#define GESPMM_ERR_CUDA         -2   /* a CUDA runtime call or the launch failed                  */
+#define GESPMM_ERR_TOO_LARGE    -3   /* M, N or nnz does not fit the int32 index contract         */
+#define GESPMM_ERR_IO           -4   /* file missing / not a MatrixMarket coordinate file        */
+#define GESPMM_ERR_WORKSPACE    -5   /* workspace too small                                       */
+#define GESPMM_ERR_NOMEM        -6   /* host allocation failed                                    */
+
+/* Library version, major*10000 + minor*100 + patch. */
+int gespmm_version(void);
+
+/* Static, human-readable text for a GESPMM_* code. */
+const char *gespmm_error_string(int code);
+
+/*
+ * C[M,K] = A[M,N] * B[N,K].
+ *   rowptr[M+1], colind[nnz]  int32, device.   rowptr[0] == 0, rowptr[M] == nnz.
+ *   val[nnz]                  fp32, device, or NULL: A is then all-ones and the row result is the
+ *                             plain sum of the gathered B rows (the "no_edge_value" kernels).
+ *   B                         fp32, device, row-major, row stride ldb >= K (reference: ldb == K).
+ *   C                         fp32, device, row-major, row stride ldc >= K.  Every element of
+ *                             C[0:M, 0:K] is written (empty rows -> 0), like the reference.
+ * Per output element the products are accumulated in CSR order into one fp32 accumulator
+ * starting from 0 (FFMA for valued, FADD for unvalued) -- the reference kernels' order --
+ * except for rows longer than GESPMM_LONG_ROW nonzeros, which are summed in 8 contiguous
+ * segments combined in fixed order (deterministic, differs from the reference only by fp32
+ * re-association).
+ * N is used for argument checking only (colind values are trusted, like the reference).
+ */
+int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
+                        const int32_t *rowptr, const int32_t *colind, const float *val,
+                        const float *B, int64_t ldb, float *C, int64_t ldc, void *stream);
+
+/* Rows with more nonzeros than this take the segmented path described above. */
+#define GESPMM_LONG_ROW 4096
+
+/*
+ * Same product with HOST buffers: allocates device buffers on `device`, copies in, runs
+ * gespmm_csr_spmm_f32, copies C back, frees, synchronises.  For callers without their own
+ * device memory management (what the CLI does by hand, spmm_test.cu:609-640).
+ */
+int gespmm_csr_spmm_f32_host(int64_t M, int64_t N, int64_t K, int64_t nnz,
+                             const int32_t *rowptr, const int32_t *colind, const float *val,
+                             const float *B, int64_t ldb, float *C, int64_t ldc, int device);
+
+/*
+ * CSR -> CSC (i.e. the CSR of A^T), the format SPMMFunction.backward needs (op.py:20-36).
+ *   in : rowptr[M+1], colind[nnz], val[nnz] (nullable)                    device
+ *   out: colptr[N+1], rowind[nnz], csc_val[nnz] (NULL iff val is NULL)    device
+ * Within a column, entries are ordered by increasing row (stable sort of the CSR order by
+ * column), which is what cusparseCsr2cscEx2 and scipy's tocsc() produce.  Deterministic.
+ * workspace: device scratch of at least gespmm_csr2csc_workspace_bytes(M, N, nnz) bytes.
+ */
+size_t gespmm_csr2csc_workspace_bytes(int64_t M, int64_t N, int64_t nnz);
+int gespmm_csr2csc_f32(int64_t M, int64_t N, int64_t nnz,
+                       const int32_t *rowptr, const int32_t *colind, const float *val,
+                       int32_t *colptr, int32_t *rowind, float *csc_val,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * MatrixMarket coordinate file -> host CSR with readMtx's post-conditions
+ * (util/util.hpp:286-333): 0-based, sorted by (row, col); `symmetric` files are mirrored and
+ * then self-loops and duplicate entries are dropped; `general` files keep both; `pattern`
+ * values are 1; `complex` files yield no entries.  Values are the file's values (the CLI
+ * then overwrites them with 1, spmm_test.cu:574 -- that is the caller's business).
+ * The three arrays are malloc'ed by the library; release them with gespmm_free_host.
+ */
+int gespmm_read_mtx(const char *path, int32_t *nrows, int32_t *ncols, int64_t *nnz,
+                    int32_t **rowptr, int32_t **colind, float **val);
+void gespmm_free_host(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GESPMM_H */

@@ -1,0 +1,204 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every symbol that
+include/gespmm.h declares, argument validation, the .mtx reader against the oracle and the
+golden fixtures, the operator module surface, generators and partitioning.  No compute calls
+(there is no GPU here and no CPU path in the product)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    from gespmm_b200 import capi
+    header = open(os.path.join(ROOT, "include", "gespmm.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(gespmm_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(capi.SYMBOLS)
+    L = capi.lib()
+    for name in declared:
+        assert getattr(L, name) is not None
+    assert capi.version() >= 100
+    assert "success" in capi.error_string(0)
+    assert "int32" in capi.error_string(capi.ERR_TOO_LARGE)
+    assert capi.LONG_ROW == int(re.search(r"#define GESPMM_LONG_ROW (\d+)", header).group(1))
+
+
+def test_library_is_sm100a_only_and_free_of_forbidden_dependencies(pkg):
+    from gespmm_b200 import build
+    out = subprocess.run(["cuobjdump", "-lelf", build.LIB], stdout=subprocess.PIPE, text=True).stdout
+    assert "sm_100a" in out and not re.search(r"sm_(?!100a)\d+", out)
+    def needed(path):
+        out = subprocess.run(["readelf", "-d", path], stdout=subprocess.PIPE, text=True).stdout
+        return re.findall(r"\(NEEDED\)\s+Shared library: \[(.*?)\]", out)
+    for lib in needed(build.LIB):
+        assert not re.search("cusparse|cublas|torch|oracle|python", lib), lib
+    ext = needed(build.EXT)
+    assert "libgespmm.so" in ext
+    assert not any(re.search("cusparse|cublas|oracle", lib) for lib in ext), ext
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "ge-spmm_b200")):
+        if os.path.basename(dirpath) in ("build", "lib", "bin", "__pycache__"):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".hpp")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|liboracle|#include\s+[\"<].*oracle", text, re.M), f
+
+
+def test_argument_validation_without_a_device(pkg):
+    """Everything that can be rejected before touching CUDA is; valid calls fail with ERR_CUDA here."""
+    from gespmm_b200 import capi
+    L = capi.lib()
+    one = ctypes.c_void_p(16)  # never dereferenced
+    f = L.gespmm_csr_spmm_f32
+    assert f(-1, 1, 1, 0, one, one, None, one, 1, one, 1, None) == capi.ERR_INVALID_ARG
+    assert f(4, 4, 8, 3, one, one, None, one, 4, one, 8, None) == capi.ERR_INVALID_ARG      # ldb < K
+    assert f(4, 4, 8, 3, None, one, None, one, 8, one, 8, None) == capi.ERR_INVALID_ARG     # null rowptr
+    assert f(4, 4, 8, 3, one, None, None, one, 8, one, 8, None) == capi.ERR_INVALID_ARG     # null colind, nnz > 0
+    assert f(2**31, 4, 8, 3, one, one, None, one, 8, one, 8, None) == capi.ERR_TOO_LARGE
+    assert f(4, 4, 8, 2**31, one, one, None, one, 8, one, 8, None) == capi.ERR_TOO_LARGE
+    assert f(0, 4, 8, 0, None, None, None, None, 8, None, 8, None) == capi.OK                 # nothing to do
+    assert f(4, 4, 0, 0, one, None, None, None, 0, None, 0, None) == capi.OK
+    assert L.gespmm_csr2csc_f32(4, 4, 3, one, one, None, one, one, None, one, 8, None) == capi.ERR_WORKSPACE
+    assert L.gespmm_csr2csc_f32(4, 4, 3, one, one, one, one, one, None, one, 1 << 30, None) == capi.ERR_INVALID_ARG
+    assert L.gespmm_csr2csc_workspace_bytes(10, 10, 1000) >= 5 * 4 * 1000
+    if not torch.cuda.is_available():
+        rp = np.zeros(5, np.int32); B = np.zeros((4, 8), np.float32); C = np.zeros((4, 8), np.float32)
+        rc = L.gespmm_csr_spmm_f32_host(4, 4, 8, 0, rp.ctypes.data, None, None, B.ctypes.data, 8, C.ctypes.data, 8, 0)
+        assert rc == capi.ERR_CUDA  # no CPU fallback
+        with pytest.raises(capi.GespmmError):
+            capi.csr_spmm_host(rp, np.zeros(0, np.int32), None, B)
+
+
+# ---- .mtx reader -----------------------------------------------------------------------------------
+
+def _csr_to_coo(rowptr, colind):
+    return np.repeat(np.arange(len(rowptr) - 1), np.diff(rowptr)), colind
+
+
+def test_reader_on_edge_cases(pkg, oracle, expected_mtx):
+    from gespmm_b200 import capi
+    for fname, exp in expected_mtx.items():
+        nr, nc, rowptr, colind, val = capi.read_mtx(os.path.join(GOLDEN, fname))
+        rows, cols = _csr_to_coo(rowptr, colind)
+        assert (nr, nc) == (exp["nrows"], exp["ncols"]), fname
+        assert rows.tolist() == exp["row"] and cols.tolist() == exp["col"], fname
+        onr, onc, orow, ocol, oval = oracle.read_mtx(os.path.join(GOLDEN, fname))
+        assert np.array_equal(rows, orow) and np.array_equal(cols, ocol), fname
+        if "symmetric" not in fname:
+            assert sorted(zip(rows.tolist(), cols.tolist(), val.tolist())) == sorted(zip(exp["row"], exp["col"], exp["val"])), fname
+
+
+@pytest.mark.parametrize("name", ["cora", "citeseer", "pubmed"])
+def test_reader_on_bundled_matrices(pkg, golden_csr, name):
+    path = "/root/reference/data/misc/%s.mtx" % name
+    if not os.path.exists(path):
+        pytest.skip("bundled .mtx only exist next to the reference")
+    from gespmm_b200 import capi
+    nr, nc, rowptr, colind, val = capi.read_mtx(path)
+    g_rowptr, g_colind, shape = golden_csr(name)
+    assert (nr, nc) == shape
+    assert np.array_equal(rowptr, g_rowptr) and np.array_equal(colind, g_colind)
+    assert (val == 1.0).all()
+
+
+def test_reader_roundtrip_through_writer_and_errors(pkg, tmp_path, golden_csr):
+    from gespmm_b200 import capi, graphs
+    rowptr, colind, shape = golden_csr("cora")
+    p = str(tmp_path / "cora_general.mtx")
+    graphs.write_mtx(p, rowptr, colind)
+    nr, nc, rp2, ci2, v2 = capi.read_mtx(p)
+    assert np.array_equal(rp2, rowptr) and np.array_equal(ci2, colind) and (v2 == 1).all()
+    rp, ci = graphs.uniform_csr(300, 200, 5000, seed=3)
+    vals = np.arange(5000) % 7 - 3
+    p = str(tmp_path / "rect_int.mtx")
+    graphs.write_mtx(p, rp, ci, N=200, field="integer", values=vals)
+    nr, nc, rp2, ci2, v2 = capi.read_mtx(p)
+    assert (nr, nc) == (300, 200)
+    assert np.array_equal(rp2, rp.numpy()) and np.array_equal(ci2, ci.numpy())
+    with pytest.raises(capi.GespmmError) as e:
+        capi.read_mtx(str(tmp_path / "missing.mtx"))
+    assert e.value.code == capi.ERR_IO
+    bad = tmp_path / "bad.mtx"
+    bad.write_text("%%NotMatrixMarket matrix coordinate real general\n1 1 0\n")
+    with pytest.raises(capi.GespmmError):
+        capi.read_mtx(str(bad))
+    arr = tmp_path / "array.mtx"
+    arr.write_text("%%MatrixMarket matrix array real general\n1 1\n1.0\n")
+    with pytest.raises(capi.GespmmError):
+        capi.read_mtx(str(arr))
+    oob = tmp_path / "oob.mtx"
+    oob.write_text("%%MatrixMarket matrix coordinate pattern general\n2 2 1\n3 1\n")
+    with pytest.raises(capi.GespmmError):
+        capi.read_mtx(str(oob))
+    cplx = tmp_path / "cplx.mtx"
+    cplx.write_text("%%MatrixMarket matrix coordinate complex general\n2 2 1\n1 1 1.0 0.0\n")
+    assert capi.read_mtx(str(cplx))[2].tolist() == [0, 0, 0]  # readMtx reads no entries for complex (util.hpp:315-320)
+
+
+# ---- operator surface ------------------------------------------------------------------------------
+
+def test_operator_module_surface(pkg):
+    from gespmm_b200 import op
+    assert sorted(n for n in dir(op.spmm) if not n.startswith("_")) == ["csr2csc", "csr_spmm", "csr_spmm_no_edge_value"]
+    assert op.spmm.__doc__.startswith("spmm in CSR format")  # spmm.cpp:97
+    rp = torch.zeros(5, dtype=torch.int32); ci = torch.zeros(0, dtype=torch.int32); B = torch.zeros(4, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):  # reference: C assert -> abort; here: exception, and no CPU path
+        op.spmm.csr_spmm_no_edge_value(rp, ci, B)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        op.spmm.csr_spmm(rp, ci, torch.zeros(0), B)
+    conv = op.GCNConv(16, 8)
+    assert repr(conv) == "GCNConv(16, 8)" and conv.weight.shape == (16, 8) and conv.bias.abs().sum() == 0
+    assert conv.weight.abs().max() <= (6.0 / 24) ** 0.5 + 1e-6
+    assert op.GCNConv(4, 4, bias=False).bias is None
+
+
+def test_generators(pkg):
+    from gespmm_b200 import graphs
+    for rp, ci, M, N in [
+        (*graphs.uniform_csr(100, 50, 1000, seed=1), 100, 50),
+        (*graphs.citation_like(N=2000, nnz=9000, seed=1), 2000, 2000),
+        (*graphs.reddit_like(seed=2, scale=0.002), None, None),
+        (*graphs.rmat(N=1000, nnz=20000, seed=4), 1000, 1000),
+    ]:
+        assert rp.dtype == torch.int32 and ci.dtype == torch.int32
+        assert rp[0] == 0 and rp[-1] == ci.numel() and (rp[1:] >= rp[:-1]).all()
+        if N:
+            assert rp.numel() == M + 1 and ci.min() >= 0 and ci.max() < N
+        rows = torch.repeat_interleave(torch.arange(rp.numel() - 1), (rp[1:] - rp[:-1]).long())
+        key = rows * (int(ci.max()) + 1) + ci
+        assert (key[1:] >= key[:-1]).all()  # sorted by (row, col)
+    a = graphs.rmat(N=1000, nnz=20000, seed=4)
+    b = graphs.rmat(N=1000, nnz=20000, seed=4)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    srp, sci = graphs.social_like(500, 4000, seed=1)  # symmetric: transpose equals itself
+    import scipy.sparse as sp
+    A = sp.csr_matrix((np.ones(sci.numel()), sci.numpy(), srp.numpy()), shape=(500, 500))
+    assert (A != A.T).nnz == 0
+    B = graphs.cli_dense(10, 10, seed=1)
+    assert B.min() >= -0.5 and B.max() <= 0.49
+
+
+def test_partition_rows(pkg):
+    from gespmm_b200 import graphs
+    from gespmm_b200.sharding import partition_rows, shard_csr
+    rp, ci = graphs.rmat(N=5000, nnz=100000, seed=4)
+    for P in (1, 2, 4, 8):
+        b = partition_rows(rp, P)
+        assert b[0] == 0 and b[-1] == 5000 and len(b) == P + 1 and all(x <= y for x, y in zip(b, b[1:]))
+        cost = [int(rp[b[i + 1]] - rp[b[i]]) + b[i + 1] - b[i] for i in range(P)]
+        assert max(cost) <= (100000 + 5000) / P + int((rp[1:] - rp[:-1]).max()) + 1
+        parts = [shard_csr(rp, ci, None, b[i], b[i + 1]) for i in range(P)]
+        assert sum(p[1].numel() for p in parts) == 100000
+        assert all(int(p[0][0]) == 0 and int(p[0][-1]) == p[1].numel() for p in parts)
+        assert torch.equal(torch.cat([p[1] for p in parts]), ci)
+    assert partition_rows(torch.zeros(1, dtype=torch.int32), 4) == [0, 0, 0, 0, 0]  # empty matrix
+    assert partition_rows(torch.zeros(11, dtype=torch.int32), 2) == [0, 5, 10]      # all rows empty: split rows
