@@ -5,47 +5,49 @@
 // their launch blocks (spmm_kernel.cu:175-207, 425-458; spmm_test.cu:456-492).  Not a
 // port: the reference maps (row, 64 columns) to a warp and walks the row serially with
 // 32-bit loads; here the unit of work is a fixed-size slice of the merged (rows + nonzeros)
-// sequence, walked as one flat stream of nonzeros with 128-bit B-panel loads.
+// sequence, walked as one flat stream of nonzeros whose B rows are gathered 512 bytes per
+// warp instruction into a shared-memory ring.
 //
-// Work decomposition
+// Work decomposition (kernel A, spmm_flat_kernel: one warp per CTA)
 //   key(r) = rowptr[r] + r is strictly increasing, so the half-open key windows
-//   [t*T, (t+1)*T) partition the rows: warp-task t owns the rows whose key falls in its
-//   window.  Every task therefore costs at most T "row stores + nonzero gathers" plus the
-//   tail of its last row, whatever the degree distribution (empty rows are work too: their
-//   C rows must be zeroed).  A task finds its rows with a 16-ary search on rowptr (both
-//   window ends at once, one per half-warp), so no per-graph preprocessing and no workspace.
+//   [t*T, (t+1)*T) partition the rows: task t owns the rows whose key falls in its window.
+//   Every task therefore costs at most T "row stores + nonzero gathers" plus the tail of its
+//   last row, whatever the degree distribution (empty rows are work too: their C rows must
+//   be zeroed).  A task finds its rows with a 16-ary search on rowptr (both window ends at
+//   once, one per half-warp): no per-graph preprocessing, no workspace.  One task = one
+//   32-thread CTA, so the hardware block scheduler is the dynamic load balancer and no warp
+//   ever waits for another.
 //
 // Flat stream
 //   A warp walks its rows' nonzeros [rowptr[row_lo], rowptr[row_hi]) in CSR order, 32 rows
-//   (one rowptr register per lane) and 32 nonzeros (one colind/val register per lane, the next
-//   32 prefetched) at a time.  (colind, val) are broadcast with __shfl and U independent
-//   128-bit loads of B-row panels are issued before the first FMA, so a warp keeps U*V*512 B
-//   of gathers in flight however short the rows are.  Row ends inside a 32-nonzero chunk are
-//   one bit mask (__reduce_or_sync over the lanes' row ends): at a set bit the C row is stored
-//   and the accumulators reset.  Each output element is accumulated in CSR order in one
-//   register, FFMA for valued / FADD for unvalued, which is the reference's order -- results
-//   are bit-identical to it.
+//   (one rowptr register per lane) and 32 nonzeros (one colind/val register per lane, two
+//   chunks prefetched) at a time.  Row ends inside a 32-nonzero chunk are one bit mask
+//   (__reduce_or_sync over the lanes' row ends): at a set bit the C row is stored and the
+//   accumulators reset.  Each output element is accumulated in CSR order in one register,
+//   FFMA for valued / FADD for unvalued, which is the reference's order -- results are
+//   bit-identical to it.
 //
-// Gather ring (the default for aligned K >= 64)
-//   In the register variant the number of B rows in flight per warp is bounded by the registers
-//   that hold them.  The ring variant takes them out of the register file: every lane copies
-//   its own 16-byte slice of each gathered B row into a per-warp shared-memory ring with
-//   cp.async (LDGSTS, no register staging), G rows per commit group, NS groups deep, and reads
-//   the same 16 bytes back with LDS.128 one group later -- lanes only ever read what they
-//   copied themselves, so cp.async.wait_group is the only synchronisation.  In-flight gather
-//   bytes per SM are then bounded by shared memory (up to ~190 KB), not by registers.
+// Gather ring (aligned operands, K % 4 == 0)
+//   Every lane copies its own 16-byte slice of each gathered B row into a per-warp
+//   shared-memory ring with cp.async (LDGSTS: no register staging), G rows per commit group,
+//   NS groups deep, and reads the same 16 bytes back with LDS.128 one group later -- lanes
+//   only ever read what they copied themselves, so cp.async.wait_group is the only
+//   synchronisation.  In-flight gather bytes per SM are bounded by shared memory (~100 KB
+//   in flight out of ~200 KB of rings), not by registers.  Unaligned operands / K % 4 != 0
+//   take the register variant (scalar loads, U rows in flight per warp).
 //
-// Long rows
-//   Rows with more than `long_row` (GESPMM_LONG_ROW) nonzeros are not walked by their owner
-//   warp.  They are queued in shared memory and, after a CTA barrier, summed by all warps of
-//   the CTA in contiguous segments whose partials are combined in fixed order through shared
-//   memory (deterministic; fp32 re-association only).
+// Long rows (kernel B, spmm_long_kernel: 8 warps per CTA)
+//   Rows with more than `long_row` nonzeros are skipped by kernel A.  Kernel B finds them
+//   without a list: every thread probes one 256-aligned nonzero position, binary-searches
+//   the row containing it, and claims that row if the row is long and the position is the
+//   first aligned one inside it.  Claimed rows are summed by all 8 warps of the CTA in
+//   contiguous segments whose partials are combined in fixed order through shared memory
+//   (deterministic; differs from the reference by fp32 re-association only).
 //
 // Column mapping
 //   Lane l owns, for v < V, the float4 at column ((v*32 + l) * 4) of the current panel
-//   (panel = 128*V columns; blockIdx.y walks panels for K > 512).  One warp-wide LDG.128
-//   therefore reads 512 contiguous bytes of a B row.  K % 4 != 0 or unaligned operands take
-//   the scalar instantiation (lane owns column v*32 + l).
+//   (panel = 128*V columns; blockIdx.y walks panels for K > 512).  One warp-wide copy
+//   therefore moves 512 contiguous bytes of a B row.
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -55,11 +57,13 @@
 
 namespace {
 
-constexpr int kMaxWarps = 8;    // warps per CTA is a template parameter NW <= kMaxWarps
-constexpr int kMaxTask = 1024;  // largest task window (keys)
-constexpr int kMinLong = 512;   // smallest accepted long-row threshold
-constexpr int kMaxLong = kMaxWarps * kMaxTask / kMinLong + 2;  // long rows that can start in one CTA's windows
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxTask = 1024;     // largest task window (keys)
+constexpr int kMinLong = 512;      // smallest accepted long-row threshold
+constexpr int kLongWarps = 8;      // warps per CTA in the long-row kernel
+constexpr int kProbeStride = 256;  // kernel B probes nonzero positions that are multiples of this (< kMinLong)
+constexpr int kProbeWindow = kLongWarps * 32 * kProbeStride;  // nonzeros covered by one CTA of kernel B
+constexpr int kMaxList = kProbeWindow / kMinLong + 2;         // long rows one CTA of kernel B can claim
 
 // ---- per-lane vector of owned columns: float4 (aligned fast path) or float (general) --------
 template <bool VEC4> struct Pack;
@@ -117,11 +121,23 @@ __device__ __forceinline__ int search_key16(const int *__restrict__ rowptr, int 
     return lo;
 }
 
+struct Operands {
+    const int *colind;
+    const float *val;
+    const float *B;
+    float *C;
+    int ldb, ldc;
+};
+
+// =================================================================================================
+// Register walker: U B-row packs in flight per lane, in registers.  Any alignment, any K.
+// =================================================================================================
 template <int V, bool VALUED, bool VEC4, int U>
 struct Walker {
     using P = Pack<VEC4>;
     using T = typename P::T;
     static constexpr int kStride = 32 * P::kWidth;  // floats between a lane's consecutive packs
+    static constexpr int kRingBytes = 0;
 
     const int *__restrict__ colind;
     const float *__restrict__ val;
@@ -131,6 +147,10 @@ struct Walker {
     unsigned vmask;                 // bit v set: this lane's v-th pack is inside K
     int lane;
 
+    __device__ __forceinline__ void init(const Operands &o, int col0, unsigned vm, int ln, unsigned /*ring*/) {
+        colind = o.colind; val = o.val; Bl = o.B + col0; Cl = o.C + col0; ldb = o.ldb; ldc = o.ldc; vmask = vm; lane = ln;
+    }
+
     __device__ __forceinline__ void store_row(int row, const T (&acc)[V]) const {
         float *c = Cl + (long long)row * ldc;
 #pragma unroll
@@ -138,8 +158,6 @@ struct Walker {
             if (vmask & (1u << v)) P::stcs(c + v * kStride, acc[v]);
     }
 
-    // One batch of U nonzeros (chunk positions j0 .. j0+U-1): all loads first, then the FMAs in
-    // CSR order with row flushes at the bits of `ends`.  FULL: every position is a real nonzero.
     template <bool FULL>
     __device__ __forceinline__ void batch(int mcol, float mval, int j0, unsigned live, unsigned ends, T (&acc)[V],
                                           unsigned &rows_left, int rb) const {
@@ -196,7 +214,7 @@ struct Walker {
             const unsigned rel = (unsigned)(my_end - 1 - p0);
             const unsigned endmask = __reduce_or_sync(kFull, (my_row && rel < 32u) ? (1u << rel) : 0u);
             const int n = min(32, e - p0);
-            const unsigned livemask = n >= 32 ? kFull : ((1u << n) - 1u);
+            const unsigned livemask = low_bits(n);
 #pragma unroll 1
             for (int j0 = 0; j0 < n; j0 += U) {
                 const unsigned live = livemask >> j0, ends = endmask >> j0;
@@ -207,19 +225,16 @@ struct Walker {
     }
 };
 
-// ---- cp.async helpers ---------------------------------------------------------------------------
+// =================================================================================================
+// Ring walker: B rows gathered into shared memory with cp.async.  float4 packs only.
+// =================================================================================================
+// CP: 0 = cp.async.cg (L2 only), 1 = cp.async.ca (allocate in L1).  (An L2 evict_last cache hint on
+// the gathers was measured too: no gain on any shape, dropped.)
 template <int CP>
-__device__ __forceinline__ void cp_async16(unsigned saddr, const float *g, unsigned long long policy)
+__device__ __forceinline__ void cp_async16(unsigned saddr, const void *g)
 {
     if (CP == 1) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(g) : "memory");
-    else if (CP == 2) asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(g), "l"(policy) : "memory");
     else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(g) : "memory");
-}
-__device__ __forceinline__ unsigned long long l2_evict_last_policy()
-{
-    unsigned long long p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
-    return p;
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -231,56 +246,86 @@ __device__ __forceinline__ float4 lds128(unsigned saddr)
     return r;
 }
 
-// Ring variant of the walker (float4 packs only).  G rows per stage, NS stages, S32 = 32/G stages
-// per 32-nonzero chunk; stage j of a chunk lives in ring slot j % NS (NS divides S32), and the
-// copies for stage j + NS - 1 are issued right before stage j is consumed.
-template <int V, bool VALUED, int G, int NS, int CP>
+// G rows per stage, NS stages (power of two, divides S32 = 32/G).  Stage j of a 32-nonzero chunk
+// lives in ring slot j % NS; the copies for stage j + NS - 1 are issued right before stage j is
+// consumed.  MASKED: some lanes' packs lie beyond K (K is not a multiple of 128*V).
+template <int V, bool VALUED, int G, int NS, int CP, bool MASKED>
 struct WalkerRing {
     using P = Pack<true>;
     using T = float4;
     static constexpr int kStride = 128;
     static constexpr int S32 = 32 / G;
     static constexpr int L = NS - 1;
+    static constexpr int UB = G < 4 ? G : 4;  // rows read back from the ring per LDS batch
     static constexpr int kStageBytes = G * V * 512;
     static constexpr int kRingBytes = NS * kStageBytes;  // per warp
-    static_assert(32 % G == 0 && S32 % NS == 0 && (NS & (NS - 1)) == 0 && L >= 1 && L <= S32, "bad ring shape");
+    static_assert(32 % G == 0 && S32 % NS == 0 && (NS & (NS - 1)) == 0 && L >= 1 && L <= S32 && G % UB == 0, "bad ring shape");
 
     const int *__restrict__ colind;
     const float *__restrict__ val;
-    const float *__restrict__ Bl;
+    const char *__restrict__ Bl;  // B + this lane's first owned column (byte pointer)
     float *__restrict__ Cl;
-    int ldb, ldc;
+    unsigned ldb_bytes;
+    int ldc;
     unsigned vmask;
     int lane;
-    unsigned ring;  // shared-space address of this lane's 16 bytes in (slot 0, row 0, pack 0)
-    unsigned long long policy;  // L2 eviction policy for the gathers (CP == 2)
+    unsigned ring;              // shared-space address of this lane's 16 bytes in (slot 0, row 0, pack 0)
+
+    __device__ __forceinline__ void init(const Operands &o, int col0, unsigned vm, int ln, unsigned ring_base) {
+        colind = o.colind; val = o.val; Bl = reinterpret_cast<const char *>(o.B + col0); Cl = o.C + col0;
+        ldb_bytes = (unsigned)o.ldb * 4u; ldc = o.ldc; vmask = vm; lane = ln;
+        ring = ring_base + ln * 16;
+    }
+
+    __device__ __forceinline__ bool pack_on(int v) const { return !MASKED || (vmask & (1u << v)); }
 
     __device__ __forceinline__ void store_row(int row, const T (&acc)[V]) const {
         float *c = Cl + (long long)row * ldc;
 #pragma unroll
         for (int v = 0; v < V; v++)
-            if (vmask & (1u << v)) P::stcs(c + v * kStride, acc[v]);
+            if (pack_on(v)) P::stcs(c + v * kStride, acc[v]);
     }
 
     // copies for the G nonzeros at chunk positions [pos0, pos0 + G) of a chunk holding n nonzeros,
     // into the stage at byte offset `slot` of the ring; always exactly one commit group
-    __device__ __forceinline__ void issue(int cols, int pos0, int n, unsigned slot) const {
+    template <bool FULL>
+    __device__ __forceinline__ void issue_impl(int cols, int pos0, int n, unsigned slot) const {
+        // addresses first, then the copies back to back (ptxas pads every LDGSTS that follows other
+        // work with three dummy LDS; consecutive LDGSTS share one such pad)
 #pragma unroll
-        for (int i = 0; i < G; i++) {
-            const int c = __shfl_sync(kFull, cols, pos0 + i);
-            if (pos0 + i < n) {
-                const float *bp = Bl + (long long)c * ldb;
+        for (int i0 = 0; i0 < G; i0 += UB) {
+            const char *bp[UB];
 #pragma unroll
-                for (int v = 0; v < V; v++)
-                    if (vmask & (1u << v)) cp_async16<CP>(ring + slot + (i * V + v) * 512, bp + v * kStride, policy);
+            for (int i = 0; i < UB; i++) {
+                const unsigned c = (unsigned)__shfl_sync(kFull, cols, pos0 + i0 + i);
+                bp[i] = Bl + (unsigned long long)c * ldb_bytes;
+            }
+#pragma unroll
+            for (int i = 0; i < UB; i++) {
+                if (FULL || pos0 + i0 + i < n) {
+#pragma unroll
+                    for (int v = 0; v < V; v++)
+                        if (pack_on(v)) cp_async16<CP>(ring + slot + ((i0 + i) * V + v) * 512, bp[i] + v * 512);
+                }
             }
         }
         cp_async_commit();
     }
+    __device__ __forceinline__ void issue(int cols, int pos0, int n, unsigned slot) const {
+        if (pos0 + G <= n) issue_impl<true>(cols, pos0, n, slot);
+        else issue_impl<false>(cols, pos0, n, slot);
+    }
 
-    __device__ __forceinline__ void consume(float vals, int pos0, int n, unsigned endmask, T (&acc)[V], unsigned &rows_left,
-                                            int rb, unsigned slot) const {
-        constexpr int UB = G < 4 ? G : 4;
+    __device__ __forceinline__ void flush(T (&acc)[V], unsigned &rows_left, int rb) const {
+        store_row(rb + __ffs(rows_left) - 1, acc);
+        rows_left &= rows_left - 1;
+#pragma unroll
+        for (int v = 0; v < V; v++) acc[v] = P::zero();
+    }
+
+    template <bool FULL>
+    __device__ __forceinline__ void consume_impl(float vals, int pos0, int n, unsigned endmask, T (&acc)[V],
+                                                 unsigned &rows_left, int rb, unsigned slot) const {
 #pragma unroll
         for (int i0 = 0; i0 < G; i0 += UB) {
             T b[UB][V];
@@ -288,30 +333,41 @@ struct WalkerRing {
 #pragma unroll
             for (int i = 0; i < UB; i++) {
                 if (VALUED) a[i] = __shfl_sync(kFull, vals, pos0 + i0 + i);
-                if (pos0 + i0 + i < n) {
+                if (FULL || pos0 + i0 + i < n) {
 #pragma unroll
                     for (int v = 0; v < V; v++)
-                        if (vmask & (1u << v)) b[i][v] = lds128(ring + slot + ((i0 + i) * V + v) * 512);
+                        if (pack_on(v)) b[i][v] = lds128(ring + slot + ((i0 + i) * V + v) * 512);
                 }
             }
+            const unsigned ends = (endmask >> (pos0 + i0)) & ((1u << UB) - 1u);
+            if (FULL && ends == 0u) {  // no row ends among these UB nonzeros: straight accumulation
 #pragma unroll
-            for (int i = 0; i < UB; i++) {
-                const int pos = pos0 + i0 + i;
-                if (pos < n) {
+                for (int i = 0; i < UB; i++) {
 #pragma unroll
                     for (int v = 0; v < V; v++) {
                         if (VALUED) P::fma(acc[v], a[i], b[i][v]);
                         else P::add(acc[v], b[i][v]);
                     }
-                    if ((endmask >> pos) & 1u) {
-                        store_row(rb + __ffs(rows_left) - 1, acc);
-                        rows_left &= rows_left - 1;
+                }
+            } else {
 #pragma unroll
-                        for (int v = 0; v < V; v++) acc[v] = P::zero();
+                for (int i = 0; i < UB; i++) {
+                    if (FULL || pos0 + i0 + i < n) {
+#pragma unroll
+                        for (int v = 0; v < V; v++) {
+                            if (VALUED) P::fma(acc[v], a[i], b[i][v]);
+                            else P::add(acc[v], b[i][v]);
+                        }
+                        if (ends & (1u << i)) flush(acc, rows_left, rb);
                     }
                 }
             }
         }
+    }
+    __device__ __forceinline__ void consume(float vals, int pos0, int n, unsigned endmask, T (&acc)[V], unsigned &rows_left,
+                                            int rb, unsigned slot) const {
+        if (pos0 + G <= n) consume_impl<true>(vals, pos0, n, endmask, acc, rows_left, rb, slot);
+        else consume_impl<false>(vals, pos0, n, endmask, acc, rows_left, rb, slot);
     }
 
     __device__ __forceinline__ void stream(int s, int e, T (&acc)[V], int my_end, unsigned rows, int rb) const {
@@ -349,56 +405,36 @@ struct WalkerRing {
     }
 };
 
-template <class WK> struct RingBytes { static constexpr int value = 0; };
-template <int V, bool VALUED, int G, int NS, int CP>
-struct RingBytes<WalkerRing<V, VALUED, G, NS, CP>> { static constexpr int value = WalkerRing<V, VALUED, G, NS, CP>::kRingBytes; };
-
-template <class WK, int V, bool VEC4, int NW, int MINB>
-__global__ void __launch_bounds__(NW * 32, MINB)
-spmm_flat_kernel(int M, int K, long long total_keys, int task, int long_row, const int *__restrict__ rowptr,
-                 const int *__restrict__ colind, const float *__restrict__ val, const float *__restrict__ B,
-                 int ldb, float *__restrict__ C, int ldc)
+// =================================================================================================
+// Kernel A: short rows.  One warp per CTA, one task per CTA.
+// =================================================================================================
+template <class WK, int V, bool VEC4, int MINB>
+__global__ void __launch_bounds__(32, MINB)
+spmm_flat_kernel(int M, int K, long long total_keys, int task, int long_row, const int *__restrict__ rowptr, Operands op)
 {
     using P = Pack<VEC4>;
     using T = typename P::T;
     constexpr int W = P::kWidth;
+    extern __shared__ __align__(16) unsigned char s_dyn[];  // gather ring (ring walker only)
 
-    __shared__ int s_long[kMaxLong];
-    __shared__ int s_nlong;
-    __shared__ T s_part[NW][V * 32];
-    extern __shared__ __align__(16) unsigned char s_dyn[];  // gather rings (ring variant only)
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) s_nlong = 0;
-    __syncthreads();
-
+    const int lane = threadIdx.x;
     const int col0 = blockIdx.y * (32 * V * W) + lane * W;
     unsigned vmask = 0;
 #pragma unroll
     for (int v = 0; v < V; v++)
         if (col0 + v * 32 * W < K) vmask |= 1u << v;
-
     WK wk;
-    wk.colind = colind; wk.val = val;
-    wk.Bl = B + col0; wk.Cl = C + col0;
-    wk.ldb = ldb; wk.ldc = ldc; wk.vmask = vmask; wk.lane = lane;
-    if constexpr (RingBytes<WK>::value > 0) {
-        wk.ring = (unsigned)__cvta_generic_to_shared(s_dyn) + warp * RingBytes<WK>::value + lane * 16;
-        wk.policy = l2_evict_last_policy();
-    }
+    wk.init(op, col0, vmask, lane, (unsigned)__cvta_generic_to_shared(s_dyn));
 
-    // ---- this warp's rows -------------------------------------------------------------------
-    const long long t = (long long)blockIdx.x * NW + warp;
-    const long long k0 = t * task;
-    int row_lo = M, row_hi = M;
+    // ---- this task's rows ---------------------------------------------------------------------
+    const long long k0 = (long long)blockIdx.x * task;
+    int row_lo, row_hi;
     {
-        // all warps run the search (it contains warp collectives); out-of-range tasks get [M, M)
         const int shift = lane & 16;
         const long long target = k0 + (shift ? task : 0);
         const int r = search_key16(rowptr, M, target < total_keys ? target : total_keys + 1, lane & 15, shift);
         row_lo = __shfl_sync(kFull, r, 0);
         row_hi = __shfl_sync(kFull, r, 16);
-        if (k0 >= total_keys) row_lo = row_hi = M;
     }
 
     for (int rb = row_lo; rb < row_hi; rb += 32) {
@@ -409,10 +445,9 @@ spmm_flat_kernel(int M, int K, long long total_keys, int task, int long_row, con
             my_end = __ldg(rowptr + rb + lane + 1);
         }
         const int len = my_end - my_start;
-        unsigned long_mask = __ballot_sync(kFull, len > long_row);
+        unsigned long_mask = __ballot_sync(kFull, len > long_row);  // left to kernel B
         const unsigned nonempty = __ballot_sync(kFull, len > 0) & ~long_mask;
-        // empty rows: zeros, one warp-wide store per row
-        {
+        {   // empty rows: zeros, one warp-wide store per row
             unsigned em = ~(nonempty | long_mask) & low_bits(nrows);
             T z[V];
 #pragma unroll
@@ -426,8 +461,7 @@ spmm_flat_kernel(int M, int K, long long total_keys, int task, int long_row, con
         int run = 0;
         while (true) {
             const int stop = long_mask ? (__ffs(long_mask) - 1) : nrows;  // next long row, or end of chunk
-            const unsigned run_bits = low_bits(stop) & ~low_bits(run);
-            const unsigned rows = nonempty & run_bits;
+            const unsigned rows = nonempty & low_bits(stop) & ~low_bits(run);
             if (rows) {
                 const int s = __shfl_sync(kFull, my_start, __ffs(rows) - 1);
                 const int e = __shfl_sync(kFull, my_end, 31 - __clz(rows));
@@ -437,74 +471,129 @@ spmm_flat_kernel(int M, int K, long long total_keys, int task, int long_row, con
                 wk.stream(s, e, acc, my_end, rows, rb);
             }
             if (stop >= nrows) break;
-            if (lane == 0) {
-                const int slot = atomicAdd(&s_nlong, 1);
-                if (slot < kMaxLong) s_long[slot] = rb + stop;
-            }
             long_mask &= long_mask - 1;
             run = stop + 1;
         }
     }
+}
 
-    // ---- long rows: all warps of the CTA, contiguous segments, fixed-order combine ----------------
+// =================================================================================================
+// Kernel B: long rows.  8 warps per CTA; claim by probing, then segmented cooperative sums.
+// =================================================================================================
+template <class WK, int V, bool VEC4>
+__global__ void __launch_bounds__(kLongWarps * 32)
+spmm_long_kernel(int M, int K, int nnz, int long_row, const int *__restrict__ rowptr, Operands op)
+{
+    using P = Pack<VEC4>;
+    using T = typename P::T;
+    constexpr int W = P::kWidth;
+    __shared__ int s_rows[kMaxList];
+    __shared__ int s_n;
+    __shared__ T s_part[2][kLongWarps][V * 32];
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
-    const int nlong = min(s_nlong, kMaxLong);
-    for (int i = 0; i < nlong; i++) {
-        const int r = s_long[i];
+
+    // ---- claim: the row containing my probe position, if long and this is its first probe --------
+    {
+        const long long p = ((long long)blockIdx.x * (kLongWarps * 32) + threadIdx.x) * kProbeStride;
+        if (p < nnz) {
+            int lo = 0, hi = M - 1;  // first r with rowptr[r + 1] > p
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(rowptr + mid + 1) > p) hi = mid;
+                else lo = mid + 1;
+            }
+            const int a = __ldg(rowptr + lo), b = __ldg(rowptr + lo + 1);
+            if (b - a > long_row && p - a < kProbeStride) {
+                const int slot = atomicAdd(&s_n, 1);
+                if (slot < kMaxList) s_rows[slot] = lo;
+            }
+        }
+    }
+    __syncthreads();
+    const int nlist = min(s_n, kMaxList);
+    if (nlist == 0) return;
+
+    const int col0 = blockIdx.y * (32 * V * W) + lane * W;
+    unsigned vmask = 0;
+#pragma unroll
+    for (int v = 0; v < V; v++)
+        if (col0 + v * 32 * W < K) vmask |= 1u << v;
+    WK wk;
+    wk.init(op, col0, vmask, lane, (unsigned)__cvta_generic_to_shared(s_dyn) + warp * WK::kRingBytes);
+
+    for (int i = 0; i < nlist; i++) {
+        const int r = s_rows[i];
         const int a = __ldg(rowptr + r), b = __ldg(rowptr + r + 1);
-        int seg = (b - a + NW - 1) / NW;
+        int seg = (b - a + kLongWarps - 1) / kLongWarps;
         seg = (seg + 31) & ~31;
         const int s = min(b, a + warp * seg), e = min(b, s + seg);
         T acc[V];
 #pragma unroll
         for (int v = 0; v < V; v++) acc[v] = P::zero();
         wk.stream(s, e, acc, 0, 0u, 0);
+        T(*part)[V * 32] = s_part[i & 1];  // double-buffered: one barrier per row
 #pragma unroll
-        for (int v = 0; v < V; v++) s_part[warp][v * 32 + lane] = acc[v];
+        for (int v = 0; v < V; v++) part[warp][v * 32 + lane] = acc[v];
         __syncthreads();
-        for (int x = threadIdx.x; x < V * 32; x += NW * 32) {
-            T sum = s_part[0][x];
+        for (int x = threadIdx.x; x < V * 32; x += kLongWarps * 32) {
+            T sum = part[0][x];
 #pragma unroll
-            for (int w = 1; w < NW; w++) P::add(sum, s_part[w][x]);
+            for (int w = 1; w < kLongWarps; w++) P::add(sum, part[w][x]);
             const int c = blockIdx.y * (32 * V * W) + x * W;
-            if (c < K) P::stcs(C + (long long)r * ldc + c, sum);
+            if (c < K) P::stcs(op.C + (long long)r * op.ldc + c, sum);
         }
-        __syncthreads();
     }
 }
 
+// =================================================================================================
+// Host side
+// =================================================================================================
 struct Args {
-    int M, K, task, long_row, ldb, ldc;
+    int M, K, task, long_row;
     long long nnz;
-    const int *rowptr, *colind;
-    const float *val, *B;
-    float *C;
+    const int *rowptr;
+    Operands op;
     cudaStream_t st;
 };
 
-template <class WK, int V, bool VEC4, int NW, int MINB>
+template <class WK, int V, bool VEC4, int MINB>
 cudaError_t launch(const Args &a)
 {
     constexpr int W = VEC4 ? 4 : 1;
-    constexpr int dyn = RingBytes<WK>::value * NW;
-    auto kern = spmm_flat_kernel<WK, V, VEC4, NW, MINB>;
-    if (dyn > 0) {
-        static cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-        if (attr != cudaSuccess) return attr;
+    const unsigned panels = (unsigned)((a.K + 32 * V * W - 1) / (32 * V * W));
+    // long rows first: they are the longest-running CTAs
+    if (a.nnz > a.long_row) {
+        constexpr int dynB = WK::kRingBytes * kLongWarps;
+        auto kernB = spmm_long_kernel<WK, V, VEC4>;
+        if (dynB > 0) {
+            static cudaError_t attr = cudaFuncSetAttribute(kernB, cudaFuncAttributeMaxDynamicSharedMemorySize, dynB);
+            if (attr != cudaSuccess) return attr;
+        }
+        dim3 grid((unsigned)((a.nnz + kProbeWindow - 1) / kProbeWindow), panels, 1);
+        kernB<<<grid, kLongWarps * 32, dynB, a.st>>>(a.M, a.K, (int)a.nnz, a.long_row, a.rowptr, a.op);
     }
+    constexpr int dynA = WK::kRingBytes;
+    auto kernA = spmm_flat_kernel<WK, V, VEC4, MINB>;
     const long long total = a.nnz + a.M;
     const long long ntask = (total + a.task - 1) / a.task;
-    dim3 grid((unsigned)((ntask + NW - 1) / NW), (unsigned)((a.K + 32 * V * W - 1) / (32 * V * W)), 1);
-    kern<<<grid, NW * 32, dyn, a.st>>>(a.M, a.K, total, a.task, a.long_row, a.rowptr, a.colind, a.val, a.B, a.ldb, a.C, a.ldc);
+    dim3 grid((unsigned)ntask, panels, 1);
+    kernA<<<grid, 32, dynA, a.st>>>(a.M, a.K, total, a.task, a.long_row, a.rowptr, a.op);
     return cudaGetLastError();
 }
 
 template <int V, bool VALUED, bool VEC4, int U, int MINB>
-cudaError_t launch_reg(const Args &a) { return launch<Walker<V, VALUED, VEC4, U>, V, VEC4, 8, MINB>(a); }
+cudaError_t launch_reg(const Args &a) { return launch<Walker<V, VALUED, VEC4, U>, V, VEC4, MINB>(a); }
 
-// CP: 0 = cp.async.cg, 1 = cp.async.ca (allocate in L1), 2 = cp.async.cg + L2 evict_last hint
-template <int V, bool VALUED, int G, int NS, int CP, int NW, int MINB>
-cudaError_t launch_ring(const Args &a) { return launch<WalkerRing<V, VALUED, G, NS, CP>, V, true, NW, MINB>(a); }
+template <int V, bool VALUED, int G, int NS, int CP, int MINB>
+cudaError_t launch_ring(const Args &a, bool masked)
+{
+    return masked ? launch<WalkerRing<V, VALUED, G, NS, CP, true>, V, true, MINB>(a)
+                  : launch<WalkerRing<V, VALUED, G, NS, CP, false>, V, true, MINB>(a);
+}
 
 int env_int(const char *name, int dflt)
 {
@@ -514,48 +603,43 @@ int env_int(const char *name, int dflt)
 
 // (V, variant) -> instantiation.  Variants other than 0 exist for tuning (GESPMM_VARIANT).
 template <bool VALUED, bool VEC4>
-cudaError_t launch_v(int V, int variant, const Args &a)
+cudaError_t launch_v(int V, int variant, bool masked, const Args &a)
 {
     if constexpr (!VEC4) {  // scalar instantiations: correctness path for odd K / unaligned operands
         switch (V) {
-            case 1: return launch_reg<1, VALUED, false, 8, 1>(a);
-            case 2: return launch_reg<2, VALUED, false, 4, 1>(a);
-            case 3: return launch_reg<3, VALUED, false, 4, 1>(a);
-            default: return launch_reg<4, VALUED, false, 4, 1>(a);
+            case 1: return launch_reg<1, VALUED, false, 8, 16>(a);
+            case 2: return launch_reg<2, VALUED, false, 4, 16>(a);
+            case 3: return launch_reg<3, VALUED, false, 4, 16>(a);
+            default: return launch_reg<4, VALUED, false, 4, 16>(a);
         }
     } else {
         switch (V) {
             case 1:
                 switch (variant) {
-                    case 1: return launch_reg<1, VALUED, true, 8, 3>(a);
-                    case 2: return launch_ring<1, VALUED, 8, 2, 0, 4, 6>(a);
-                    case 3: return launch_ring<1, VALUED, 4, 2, 0, 8, 4>(a);
-                    case 4: return launch_ring<1, VALUED, 4, 2, 0, 4, 8>(a);
-                    case 5: return launch_ring<1, VALUED, 8, 2, 2, 8, 3>(a);
-                    case 6: return launch_ring<1, VALUED, 8, 2, 2, 4, 6>(a);
-                    case 7: return launch_ring<1, VALUED, 8, 2, 1, 8, 3>(a);
-                    case 8: return launch_ring<1, VALUED, 16, 2, 0, 4, 3>(a);
-                    default: return launch_ring<1, VALUED, 8, 2, 0, 8, 3>(a);
+                    case 1: return launch_reg<1, VALUED, true, 8, 24>(a);
+                    case 2: return launch_ring<1, VALUED, 4, 2, 0, 32>(a, masked);
+                    case 3: return launch_ring<1, VALUED, 8, 4, 0, 12>(a, masked);
+                    case 4: return launch_ring<1, VALUED, 16, 2, 0, 12>(a, masked);
+                    case 6: return launch_ring<1, VALUED, 8, 2, 1, 24>(a, masked);
+                    default: return launch_ring<1, VALUED, 8, 2, 0, 24>(a, masked);
                 }
             case 2:
                 switch (variant) {
-                    case 1: return launch_reg<2, VALUED, true, 4, 3>(a);
-                    case 2: return launch_ring<2, VALUED, 4, 2, 0, 4, 6>(a);
-                    case 3: return launch_ring<2, VALUED, 2, 2, 0, 8, 4>(a);
-                    case 5: return launch_ring<2, VALUED, 4, 2, 2, 8, 3>(a);
-                    default: return launch_ring<2, VALUED, 4, 2, 0, 8, 3>(a);
+                    case 1: return launch_reg<2, VALUED, true, 4, 24>(a);
+                    case 2: return launch_ring<2, VALUED, 2, 2, 0, 32>(a, masked);
+                    case 3: return launch_ring<2, VALUED, 8, 2, 0, 12>(a, masked);
+                    default: return launch_ring<2, VALUED, 4, 2, 0, 20>(a, masked);
                 }
             case 3:
                 switch (variant) {
-                    case 1: return launch_reg<3, VALUED, true, 2, 2>(a);
-                    default: return launch_ring<3, VALUED, 2, 2, 0, 8, 3>(a);
+                    case 1: return launch_reg<3, VALUED, true, 2, 16>(a);
+                    default: return launch_ring<3, VALUED, 2, 2, 0, 24>(a, masked);
                 }
             default:
                 switch (variant) {
-                    case 1: return launch_reg<4, VALUED, true, 2, 2>(a);
-                    case 2: return launch_ring<4, VALUED, 2, 2, 0, 4, 6>(a);
-                    case 5: return launch_ring<4, VALUED, 2, 2, 2, 8, 3>(a);
-                    default: return launch_ring<4, VALUED, 2, 2, 0, 8, 3>(a);
+                    case 1: return launch_reg<4, VALUED, true, 2, 16>(a);
+                    case 3: return launch_ring<4, VALUED, 4, 2, 0, 12>(a, masked);
+                    default: return launch_ring<4, VALUED, 2, 2, 0, 16>(a, masked);
                 }
         }
     }
@@ -568,7 +652,7 @@ extern "C" int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
                                    float *C, int64_t ldc, void *stream)
 {
     if (M < 0 || N < 0 || K < 0 || nnz < 0) return GESPMM_ERR_INVALID_ARG;
-    if (M > INT32_MAX - 64 || N > INT32_MAX || nnz > INT32_MAX - 64 || K > INT32_MAX || ldb > INT32_MAX || ldc > INT32_MAX)
+    if (M > INT32_MAX - 64 || N > INT32_MAX || nnz > INT32_MAX - 64 || K > INT32_MAX || ldb >= (1LL << 30) || ldc > INT32_MAX)
         return GESPMM_ERR_TOO_LARGE;
     if (M == 0 || K == 0) return GESPMM_OK;
     if (ldb < K || ldc < K) return GESPMM_ERR_INVALID_ARG;
@@ -578,10 +662,11 @@ extern "C" int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
     const bool vec4 = (K % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) &&
                       ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
     const int W = vec4 ? 4 : 1;
-    const int panels = (int)((K + 32 * W - 1) / (32 * W));
-    const int V = panels >= 4 ? 4 : panels;
+    const int packs = (int)((K + 32 * W - 1) / (32 * W));
+    const int V = packs >= 4 ? 4 : packs;
+    const bool masked = (K % (32 * W * V)) != 0;  // some lanes' packs fall beyond K
 
-    // Task window (keys per warp): sized so the grid is ~40 waves of resident CTAs -- small enough
+    // Task window (keys per task): sized so the grid is ~40 waves of resident CTAs -- small enough
     // that the tail of the last wave is negligible, large enough (<= 512) that a task's start-up
     // (row search, first rowptr/colind fetch) is amortised.  Measured on B200: 128 is best for the
     // 20 M-key cit-Patents shape, 512 for the 100-200 M-key Reddit / products / R-MAT shapes.
@@ -590,7 +675,7 @@ extern "C" int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
     const int forced_long = env_int("GESPMM_LONG", 0);
     const int variant = env_int("GESPMM_VARIANT", 0);
     const long long total = nnz + M;
-    const long long warps_per_wave = 148LL * 3 * kMaxWarps;
+    const long long warps_per_wave = 148LL * 24;
     long long tk = total / (40 * warps_per_wave);
     tk &= ~31LL;
     int task = (int)(tk < 32 ? 32 : (tk > 512 ? 512 : tk));
@@ -599,11 +684,11 @@ extern "C" int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
     if (forced_long >= kMinLong) long_row = forced_long;
 
     Args a;
-    a.M = (int)M; a.K = (int)K; a.task = task; a.long_row = long_row; a.ldb = (int)ldb; a.ldc = (int)ldc;
-    a.nnz = nnz; a.rowptr = rowptr; a.colind = colind; a.val = val; a.B = B; a.C = C;
+    a.M = (int)M; a.K = (int)K; a.task = task; a.long_row = long_row; a.nnz = nnz; a.rowptr = rowptr;
+    a.op.colind = colind; a.op.val = val; a.op.B = B; a.op.C = C; a.op.ldb = (int)ldb; a.op.ldc = (int)ldc;
     a.st = static_cast<cudaStream_t>(stream);
     cudaError_t err;
-    if (val) err = vec4 ? launch_v<true, true>(V, variant, a) : launch_v<true, false>(V, variant, a);
-    else err = vec4 ? launch_v<false, true>(V, variant, a) : launch_v<false, false>(V, variant, a);
+    if (val) err = vec4 ? launch_v<true, true>(V, variant, masked, a) : launch_v<true, false>(V, variant, masked, a);
+    else err = vec4 ? launch_v<false, true>(V, variant, masked, a) : launch_v<false, false>(V, variant, masked, a);
     return err == cudaSuccess ? GESPMM_OK : GESPMM_ERR_CUDA;
 }

@@ -66,7 +66,7 @@ const char *gespmm_error_string(int code);
  * Per output element the products are accumulated in CSR order into one fp32 accumulator
  * starting from 0 (FFMA for valued, FADD for unvalued) -- the reference kernels' order --
  * except for rows longer than GESPMM_LONG_ROW nonzeros, which are summed in 8 contiguous
- * segments (one per warp of the CTA) combined in fixed order (deterministic, differs from the reference only by fp32
+ * segments (one per warp of a CTA) combined in fixed order (deterministic, differs from the reference only by fp32
  * re-association).
  * N is used for argument checking only (colind values are trusted, like the reference).
  */
@@ -75,7 +75,7 @@ int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
                         const float *B, int64_t ldb, float *C, int64_t ldc, void *stream);
 
 /* Rows with more nonzeros than this take the segmented path described above. */
-#define GESPMM_LONG_ROW 512
+#define GESPMM_LONG_ROW 2048
 
 /*
  * Same product with HOST buffers: allocates device buffers on `device`, copies in, runs

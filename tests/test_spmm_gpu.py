@@ -19,7 +19,7 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-4  # BASELINE.json north_star: "within 1e-4 relative fp32"
-LONG = 512  # GESPMM_LONG_ROW (include/gespmm.h); test_host checks capi.LONG_ROW against the header
+LONG = 2048  # GESPMM_LONG_ROW (include/gespmm.h); test_host checks capi.LONG_ROW against the header
 
 
 @pytest.fixture(scope="module")
