@@ -202,17 +202,36 @@ def run_reference_arm(args):
     dt = (time.perf_counter() - t0) / args.steps
     val = 2.0 * s_nnz * K / dt / 1e9
     sample = "rows [0,%d) of %d, nnz %d of %d per step" % (rows, M, s_nnz, nnz)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "spmm_gflops", "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload], "K": K, "M": M, "nnz": nnz, "valued": True, "scale": args.scale},
         "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": oracle.num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Route everything written to fd 1 (e.g. NCCL's version banner, library chatter) to stderr and keep
+    the real stdout for the one JSON line the driver parses."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    (_REAL_STDOUT or sys.stdout).write(json.dumps(obj) + "\n")
+    (_REAL_STDOUT or sys.stdout).flush()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
@@ -276,6 +295,10 @@ def main():
     if rank != 0:
         del rowptr, colind
     M_loc, nnz_loc = sh.row_hi - sh.row_lo, sh.nnz_local
+    per_rank_shape = [[M_loc, nnz_loc]]
+    if world > 1:
+        t = torch.zeros(world, 2, device=dev, dtype=torch.int64); t[rank, 0] = M_loc; t[rank, 1] = nnz_loc
+        dist.all_reduce(t); per_rank_shape = t.tolist()
 
     def step():
         return sh.forward(B)
@@ -306,6 +329,9 @@ def main():
     ms_total = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms_total], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_total = float(t)
+    per_rank_ms = [e0.elapsed_time(e1) / args.steps]
+    if world > 1:
+        t = torch.zeros(world, device=dev); t[rank] = per_rank_ms[0]; dist.all_reduce(t); per_rank_ms = [round(float(x), 4) for x in t]
     ms = ms_total / args.steps
     clocks = sampler.stop() if sampler else None
     flops = 2.0 * nnz * K
@@ -325,7 +351,8 @@ def main():
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
-                "traffic": traffic, "peak_source": peak_src, "bytes_min": bm,
+                "traffic": traffic, "traffic_unit": "bytes per step, ncu dram__bytes_read.sum + dram__bytes_write.sum of both kernels (profiles/traffic.json)",
+                "peak_source": peak_src, "bytes_min": bm,
                 "frac_of_8TBs_nominal": achieved / (8000.0 * world),
                 # secondary, labelled: no-B-reuse model, every nonzero gathers its own B row from DRAM
                 "bytes_gather_model": 4.0 * (M + world) + 4.0 * nnz * (1 if args.unvalued else 2) + 4.0 * nnz * K + 4.0 * M * K}
@@ -398,8 +425,9 @@ def main():
                    "scale": args.scale, "sharding": "nnz-balanced contiguous row blocks, B replicated by one NCCL broadcast before the timed region" if world > 1 else "none",
                    "l2": "inputs larger than L2 (B + C = %.2f GB per rank vs 126 MB)" % ((N * K + M_loc * K) * 4 / 1e9),
                    "degree_stats": stats},
-        "roofline": roofline, "e2e": e2e, "gpu_launches": args.steps * (2 if nnz_loc > 2048 else 1), "clocks": clocks,
-        "b_broadcast_ms": bcast_ms if world > 1 else None,
+        "roofline": roofline, "e2e": e2e, "gpu_launches": args.steps * (2 if nnz_loc > 4096 else 1), "clocks": clocks,
+        "b_broadcast_ms": bcast_ms if world > 1 else None, "per_rank_ms": per_rank_ms,
+        "per_rank_rows_nnz": per_rank_shape,
     }
 
     if rank == 0:
@@ -418,7 +446,7 @@ def main():
                     Cl = step()
                     Crl = Cr[sh.row_lo:sh.row_hi]
                     same = bool(torch.equal(Crl, Cl))
-                    short = ((rowptr_full[1:] - rowptr_full[:-1]) <= 2048)[sh.row_lo:sh.row_hi]
+                    short = ((rowptr_full[1:] - rowptr_full[:-1]) <= 4096)[sh.row_lo:sh.row_hi]
                     same_short = bool(torch.equal(Crl[short], Cl[short]))
                     maxdiff = float((Crl - Cl).abs().max())
                     out["reference_kernel_same_gpu"] = {
@@ -432,7 +460,7 @@ def main():
                 out["reference_kernel_same_gpu"] = {"unavailable": "oracle/_ref not built or int32 offsets would overflow"}
         if not args.no_cpu and world == 1:  # rank 0 at N = 1 only
             out["cpu_baseline"] = cpu_legs(rowptr_full, colind_full, B, K)
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -14,7 +14,7 @@ from . import build as _build
 
 OK = 0
 ERR_INVALID_ARG, ERR_CUDA, ERR_TOO_LARGE, ERR_IO, ERR_WORKSPACE, ERR_NOMEM = -1, -2, -3, -4, -5, -6
-LONG_ROW = 2048
+LONG_ROW = 4096
 
 # every symbol include/gespmm.h declares
 SYMBOLS = (

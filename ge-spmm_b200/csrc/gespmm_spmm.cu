@@ -42,13 +42,18 @@
 //   the row containing it, and claims that row if the row is long and the position is the
 //   first aligned one inside it.  Claimed rows are summed by all 8 warps of the CTA in
 //   contiguous segments whose partials are combined in fixed order through shared memory
-//   (deterministic; differs from the reference by fp32 re-association only).
+//   (deterministic; differs from the reference by fp32 re-association only).  Rows of at least
+//   32768 nonzeros (R-MAT hubs) are summed by the whole 8-CTA thread-block cluster -- 64
+//   segments, CTA partials combined in rank order through distributed shared memory -- so the
+//   longest row of the matrix does not become the tail of the launch.  Kernel B runs on a
+//   helper stream, concurrently with kernel A.
 //
 // Column mapping
 //   Lane l owns, for v < V, the float4 at column ((v*32 + l) * 4) of the current panel
 //   (panel = 128*V columns; blockIdx.y walks panels for K > 512).  One warp-wide copy
 //   therefore moves 512 contiguous bytes of a B row.
 
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -64,6 +69,9 @@ constexpr int kLongWarps = 8;      // warps per CTA in the long-row kernel
 constexpr int kProbeStride = 256;  // kernel B probes nonzero positions that are multiples of this (< kMinLong)
 constexpr int kProbeWindow = kLongWarps * 32 * kProbeStride;  // nonzeros covered by one CTA of kernel B
 constexpr int kMaxList = kProbeWindow / kMinLong + 2;         // long rows one CTA of kernel B can claim
+constexpr int kClusterSize = 8;    // CTAs per cluster in kernel B (portable maximum)
+constexpr int kHugeRow = 32768;    // rows at least this long are summed by a whole cluster (64 warps)
+constexpr int kMaxHuge = kProbeWindow / kHugeRow + 2;         // huge rows one CTA of kernel B can claim
 
 // ---- per-lane vector of owned columns: float4 (aligned fast path) or float (general) --------
 template <bool VEC4> struct Pack;
@@ -478,22 +486,28 @@ spmm_flat_kernel(int M, int K, long long total_keys, int task, int long_row, con
 }
 
 // =================================================================================================
-// Kernel B: long rows.  8 warps per CTA; claim by probing, then segmented cooperative sums.
+// Kernel B: long rows.  8 warps per CTA, clusters of 8 CTAs.  Claim by probing, then segmented
+// cooperative sums: one CTA per long row, the whole cluster (64 warps, partials combined through
+// distributed shared memory) per huge row.
 // =================================================================================================
 template <class WK, int V, bool VEC4>
-__global__ void __launch_bounds__(kLongWarps * 32)
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kLongWarps * 32)
 spmm_long_kernel(int M, int K, int nnz, int long_row, const int *__restrict__ rowptr, Operands op)
 {
+    namespace cg = cooperative_groups;
     using P = Pack<VEC4>;
     using T = typename P::T;
     constexpr int W = P::kWidth;
     __shared__ int s_rows[kMaxList];
-    __shared__ int s_n;
+    __shared__ int s_huge[kMaxHuge];
+    __shared__ int s_n, s_nhuge;
     __shared__ T s_part[2][kLongWarps][V * 32];
+    __shared__ T s_cpart[V * 32];  // this CTA's partial of a huge row, read by cluster rank 0
     extern __shared__ __align__(16) unsigned char s_dyn[];
 
+    cg::cluster_group cluster = cg::this_cluster();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) s_n = 0;
+    if (threadIdx.x == 0) { s_n = 0; s_nhuge = 0; }
     __syncthreads();
 
     // ---- claim: the row containing my probe position, if long and this is its first probe --------
@@ -508,14 +522,17 @@ spmm_long_kernel(int M, int K, int nnz, int long_row, const int *__restrict__ ro
             }
             const int a = __ldg(rowptr + lo), b = __ldg(rowptr + lo + 1);
             if (b - a > long_row && p - a < kProbeStride) {
-                const int slot = atomicAdd(&s_n, 1);
-                if (slot < kMaxList) s_rows[slot] = lo;
+                if (b - a >= kHugeRow) {
+                    const int slot = atomicAdd(&s_nhuge, 1);
+                    if (slot < kMaxHuge) s_huge[slot] = lo;
+                } else {
+                    const int slot = atomicAdd(&s_n, 1);
+                    if (slot < kMaxList) s_rows[slot] = lo;
+                }
             }
         }
     }
     __syncthreads();
-    const int nlist = min(s_n, kMaxList);
-    if (nlist == 0) return;
 
     const int col0 = blockIdx.y * (32 * V * W) + lane * W;
     unsigned vmask = 0;
@@ -525,6 +542,8 @@ spmm_long_kernel(int M, int K, int nnz, int long_row, const int *__restrict__ ro
     WK wk;
     wk.init(op, col0, vmask, lane, (unsigned)__cvta_generic_to_shared(s_dyn) + warp * WK::kRingBytes);
 
+    // ---- long rows: this CTA's 8 warps, contiguous segments, fixed-order combine ------------------
+    const int nlist = min(s_n, kMaxList);
     for (int i = 0; i < nlist; i++) {
         const int r = s_rows[i];
         const int a = __ldg(rowptr + r), b = __ldg(rowptr + r + 1);
@@ -547,6 +566,46 @@ spmm_long_kernel(int M, int K, int nnz, int long_row, const int *__restrict__ ro
             if (c < K) P::stcs(op.C + (long long)r * op.ldc + c, sum);
         }
     }
+
+    // ---- huge rows: all 64 warps of the cluster; CTA partials meet in cluster rank 0 via DSMEM -----
+    cluster.sync();  // every CTA's huge list is complete and visible cluster-wide
+    const unsigned crank = cluster.block_rank(), csize = cluster.num_blocks();
+    for (unsigned q = 0; q < csize; q++) {
+        const int cnt = min(*cluster.map_shared_rank(&s_nhuge, q), kMaxHuge);
+        const int *list = cluster.map_shared_rank(s_huge, q);
+        for (int i = 0; i < cnt; i++) {
+            const int r = list[i];
+            const int a = __ldg(rowptr + r), b = __ldg(rowptr + r + 1);
+            const int nseg = (int)csize * kLongWarps;
+            int seg = (b - a + nseg - 1) / nseg;
+            seg = (seg + 31) & ~31;
+            const int s = min(b, a + ((int)crank * kLongWarps + warp) * seg), e = min(b, s + seg);
+            T acc[V];
+#pragma unroll
+            for (int v = 0; v < V; v++) acc[v] = P::zero();
+            wk.stream(s, e, acc, 0, 0u, 0);
+#pragma unroll
+            for (int v = 0; v < V; v++) s_part[0][warp][v * 32 + lane] = acc[v];
+            __syncthreads();
+            for (int x = threadIdx.x; x < V * 32; x += kLongWarps * 32) {
+                T sum = s_part[0][0][x];
+#pragma unroll
+                for (int w = 1; w < kLongWarps; w++) P::add(sum, s_part[0][w][x]);
+                s_cpart[x] = sum;
+            }
+            cluster.sync();  // all CTA partials written
+            if (crank == 0) {
+                for (int x = threadIdx.x; x < V * 32; x += kLongWarps * 32) {
+                    T sum = s_cpart[x];
+                    for (unsigned c2 = 1; c2 < csize; c2++) P::add(sum, cluster.map_shared_rank(s_cpart, c2)[x]);
+                    const int c = blockIdx.y * (32 * V * W) + x * W;
+                    if (c < K) P::stcs(op.C + (long long)r * op.ldc + c, sum);
+                }
+            }
+            cluster.sync();  // partials consumed: s_part / s_cpart may be rewritten
+        }
+    }
+    cluster.sync();  // nobody exits while its shared memory may still be read by a peer
 }
 
 // =================================================================================================
@@ -554,27 +613,65 @@ spmm_long_kernel(int M, int K, int nnz, int long_row, const int *__restrict__ ro
 // =================================================================================================
 struct Args {
     int M, K, task, long_row;
+    bool overlap;  // run kernel B concurrently with kernel A (helper stream)
     long long nnz;
     const int *rowptr;
     Operands op;
     cudaStream_t st;
 };
 
+// Kernel B runs on a helper stream, forked from and joined back into the caller's stream with
+// events, so that its long-running CTAs overlap kernel A instead of leaving the GPU idle behind
+// their tail.  One helper stream + two events per (host thread, device), created on first use;
+// the fork/join pattern is legal under stream capture, so the call stays graph-capturable.
+struct Side {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool ok = false;
+};
+constexpr int kMaxDevices = 64;
+
+Side *side_for_current_device()
+{
+    thread_local Side sides[kMaxDevices];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    Side &sd = sides[dev];
+    if (!sd.ok) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = greatest priority: the long rows should be placed first
+        if (cudaStreamCreateWithPriority(&sd.stream, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        sd.ok = true;
+    }
+    return &sd;
+}
+
 template <class WK, int V, bool VEC4, int MINB>
 cudaError_t launch(const Args &a)
 {
     constexpr int W = VEC4 ? 4 : 1;
     const unsigned panels = (unsigned)((a.K + 32 * V * W - 1) / (32 * V * W));
-    // long rows first: they are the longest-running CTAs
-    if (a.nnz > a.long_row) {
+    const bool has_b = a.nnz > a.long_row;
+    Side *sd = (has_b && a.overlap) ? side_for_current_device() : nullptr;
+    if (has_b) {
         constexpr int dynB = WK::kRingBytes * kLongWarps;
         auto kernB = spmm_long_kernel<WK, V, VEC4>;
         if (dynB > 0) {
             static cudaError_t attr = cudaFuncSetAttribute(kernB, cudaFuncAttributeMaxDynamicSharedMemorySize, dynB);
             if (attr != cudaSuccess) return attr;
         }
-        dim3 grid((unsigned)((a.nnz + kProbeWindow - 1) / kProbeWindow), panels, 1);
-        kernB<<<grid, kLongWarps * 32, dynB, a.st>>>(a.M, a.K, (int)a.nnz, a.long_row, a.rowptr, a.op);
+        cudaStream_t sb = a.st;
+        if (sd) {
+            if (cudaEventRecord(sd->fork, a.st) != cudaSuccess || cudaStreamWaitEvent(sd->stream, sd->fork, 0) != cudaSuccess)
+                return cudaGetLastError();
+            sb = sd->stream;
+        }
+        const unsigned ctas = (unsigned)((a.nnz + kProbeWindow - 1) / kProbeWindow);
+        dim3 grid((ctas + kClusterSize - 1) / kClusterSize * kClusterSize, panels, 1);  // whole clusters
+        kernB<<<grid, kLongWarps * 32, dynB, sb>>>(a.M, a.K, (int)a.nnz, a.long_row, a.rowptr, a.op);
+        if (sd && cudaEventRecord(sd->join, sd->stream) != cudaSuccess) return cudaGetLastError();
     }
     constexpr int dynA = WK::kRingBytes;
     auto kernA = spmm_flat_kernel<WK, V, VEC4, MINB>;
@@ -582,6 +679,7 @@ cudaError_t launch(const Args &a)
     const long long ntask = (total + a.task - 1) / a.task;
     dim3 grid((unsigned)ntask, panels, 1);
     kernA<<<grid, 32, dynA, a.st>>>(a.M, a.K, total, a.task, a.long_row, a.rowptr, a.op);
+    if (sd && cudaStreamWaitEvent(a.st, sd->join, 0) != cudaSuccess) return cudaGetLastError();
     return cudaGetLastError();
 }
 
@@ -687,6 +785,7 @@ extern "C" int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
     a.M = (int)M; a.K = (int)K; a.task = task; a.long_row = long_row; a.nnz = nnz; a.rowptr = rowptr;
     a.op.colind = colind; a.op.val = val; a.op.B = B; a.op.C = C; a.op.ldb = (int)ldb; a.op.ldc = (int)ldc;
     a.st = static_cast<cudaStream_t>(stream);
+    a.overlap = env_int("GESPMM_OVERLAP", 1) != 0;
     cudaError_t err;
     if (val) err = vec4 ? launch_v<true, true>(V, variant, masked, a) : launch_v<true, false>(V, variant, masked, a);
     else err = vec4 ? launch_v<false, true>(V, variant, masked, a) : launch_v<false, false>(V, variant, masked, a);

@@ -25,7 +25,9 @@
  *   - All device pointers must live on the device that is current when the call is made.
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, which is what
  *     the reference launches on: spmm_kernel.cu:189,196,203).  Calls are asynchronous on it.
- *   - No allocation and no hidden state inside gespmm_csr_spmm_f32: re-entrant, graph-capturable.
+ *   - gespmm_csr_spmm_f32 allocates no memory and takes no workspace; its only state is one helper
+ *     stream per (host thread, device), created on first use, on which the long-row kernel overlaps
+ *     the main kernel (forked from / joined into `stream` with events).  Re-entrant, graph-capturable.
  *   - Return value: GESPMM_OK or a negative GESPMM_ERR_* code.  Never exits the process
  *     (the reference's checkCudaError macros call exit(): spmm_kernel.cu:5-19).
  *   - There is NO CPU fallback: without a CUDA device every compute entry point fails with
@@ -75,7 +77,7 @@ int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
                         const float *B, int64_t ldb, float *C, int64_t ldc, void *stream);
 
 /* Rows with more nonzeros than this take the segmented path described above. */
-#define GESPMM_LONG_ROW 2048
+#define GESPMM_LONG_ROW 4096
 
 /*
  * Same product with HOST buffers: allocates device buffers on `device`, copies in, runs

@@ -19,7 +19,7 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-4  # BASELINE.json north_star: "within 1e-4 relative fp32"
-LONG = 2048  # GESPMM_LONG_ROW (include/gespmm.h); test_host checks capi.LONG_ROW against the header
+LONG = 4096  # GESPMM_LONG_ROW (include/gespmm.h); test_host checks capi.LONG_ROW against the header
 
 
 @pytest.fixture(scope="module")
@@ -163,14 +163,14 @@ def test_long_rows_segmented_path(spmm, dev, oracle, K):
     rng = np.random.default_rng(K)
     M, N = 600, 5000
     deg = rng.integers(0, 12, M)
-    deg[[0, 17, 18, 300, 599]] = [30000, LONG + 1, LONG, 12345, 8191]
+    deg[[0, 17, 18, 300, 301, 599]] = [70000, LONG + 1, LONG, 12345, 32768, 40001]  # 32768+: whole-cluster path
     rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
     colind = rng.integers(0, N, rowptr[-1]).astype(np.int32)
     B = oracle.fill_B_cli(N * K, seed=1).reshape(N, K)
     val = rng.standard_normal(rowptr[-1]).astype(np.float32)
     for v in (None, val):
         C1 = _run(spmm, dev, rowptr, colind, v, B)
-        assert _check(oracle, rowptr, colind, v, B, C1) == 4
+        assert _check(oracle, rowptr, colind, v, B, C1) == 5
         C2 = _run(spmm, dev, rowptr, colind, v, B)
         assert torch.equal(C1, C2), "segmented path must be deterministic"
 
