@@ -12,7 +12,11 @@ Differences, all deliberate:
     which this image does not have);
   * forward does not stash ``feat`` in ctx (op.py:16 keeps [N,K] alive for nothing);
   * ``normalize=False`` works (op.py:131-134 calls ``rowptr.shape(0)``, a TypeError);
-  * the "[I] Treat edge weight as no_grad." notice (op.py:31) is printed once, not per call.
+  * the "[I] Treat edge weight as no_grad." notice (op.py:31) is printed once, not per call;
+  * ``GCNConv(..., fuse_norm=True)`` (new, off by default) folds the two degree-normalisation
+    passes around the aggregation (op.py:142,145: ``x * out_deg_norm`` before, ``* in_deg_norm``
+    after, 2 x N x K x 4 bytes each way) into the edge values of the valued kernel:
+    w[p] = in_norm[row(p)] * ew[p] * out_norm[col(p)], computed once and cached.
 """
 import importlib
 import math
@@ -85,11 +89,21 @@ def zeros(tensor):
         tensor.data.fill_(0)
 
 
+def _fused_edge_weights(indptr, indices, row_norm, col_norm, ew):
+    """w[p] = row_norm[row(p)] * ew[p] * col_norm[indices[p]] for a CSR given by (indptr, indices)."""
+    deg = (indptr[1:] - indptr[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(deg.numel(), device=indptr.device), deg)
+    w = row_norm.reshape(-1)[rows] * col_norm.reshape(-1)[indices.long()]
+    return (w if ew is None else w * ew).contiguous()
+
+
 class GCNConv(torch.nn.Module):
     """x' = D_in^-1/2 A D_out^-1/2 (x W) + b, aggregation through SPMMFunction (op.py:77-152)."""
 
-    def __init__(self, in_channels, out_channels, improved=False, cached=False, bias=True, normalize=True, **kwargs):
+    def __init__(self, in_channels, out_channels, improved=False, cached=False, bias=True, normalize=True,
+                 fuse_norm=False, **kwargs):
         super().__init__()
+        self.fuse_norm = fuse_norm
         self.in_channels = in_channels
         self.out_channels = out_channels
         self.improved = improved
@@ -107,6 +121,7 @@ class GCNConv(torch.nn.Module):
         zeros(self.bias)
         self.cached_result = None
         self.cached_num_edges = None
+        self.cached_fused = None
 
     @staticmethod
     def in_deg_sqrt(indptr):
@@ -127,6 +142,13 @@ class GCNConv(torch.nn.Module):
                 out_deg_norm = torch.ones(colptr.shape[0] - 1, 1, dtype=x.dtype, device=x.device)
             self.cached_result = in_deg_norm, out_deg_norm
         in_deg_norm, out_deg_norm = self.cached_result
+        if self.normalize and self.fuse_norm:
+            if not self.cached or self.cached_fused is None:
+                self.cached_fused = (_fused_edge_weights(rowptr, colind, in_deg_norm, out_deg_norm, edge_weight_csr),
+                                     _fused_edge_weights(colptr, rowind, out_deg_norm, in_deg_norm, edge_weight_csc))
+            w_csr, w_csc = self.cached_fused
+            aggr_out = SPMMFunction.apply(rowptr, colind, colptr, rowind, x, w_csr, w_csc)
+            return aggr_out if self.bias is None else aggr_out + self.bias
         if self.normalize:
             x = x * out_deg_norm
         aggr_out = SPMMFunction.apply(rowptr, colind, colptr, rowind, x, edge_weight_csr, edge_weight_csc)

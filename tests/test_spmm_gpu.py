@@ -362,6 +362,31 @@ def test_gcnconv_matches_dense(dev, pkg):
     assert x.grad is not None and conv.weight.grad is not None and torch.isfinite(x.grad).all()
 
 
+def test_gcnconv_fused_norm_and_training_loop(dev, pkg):
+    """fuse_norm folds the degree normalisation into the valued kernel's edge weights: same layer output;
+    the 2-layer training loop (the reference's gcn_custom.py on the real PubMed adjacency) learns."""
+    import importlib.util
+    from gespmm_b200.op import GCNConv
+    spec = importlib.util.spec_from_file_location("gcn_custom", os.path.join(ROOT, "ge-spmm_b200", "gcn_custom.py"))
+    gcn = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gcn)
+    g, x, y, masks, n_in, n_out = gcn.load_problem(dev)
+    a = (g["rowptr"], g["colind"], g["colptr"], g["rowind"], g["value_csr"], g["value_csc"])
+    torch.manual_seed(1)
+    plain = GCNConv(n_in, 32, cached=True).to(dev)
+    fused = GCNConv(n_in, 32, cached=True, fuse_norm=True).to(dev)
+    fused.load_state_dict(plain.state_dict())
+    xg1, xg2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    o1, o2 = plain(xg1, *a), fused(xg2, *a)
+    assert torch.allclose(o1, o2, rtol=1e-4, atol=1e-6)
+    o1.square().sum().backward(); o2.square().sum().backward()
+    assert torch.allclose(xg1.grad, xg2.grad, rtol=1e-3, atol=1e-7)
+    assert torch.allclose(plain.weight.grad, fused.weight.grad, rtol=1e-3, atol=1e-6)
+    for fuse in (False, True):
+        res = gcn.run(n_hidden=16, layers=2, epochs=40, fuse_norm=fuse, log=lambda *_: None)
+        assert res["last_loss"] < 0.7 * res["first_loss"] and res["best_val"] > 0.5, res
+
+
 # ---- CLI ---------------------------------------------------------------------------------------------
 
 def test_cli_contract(tmp_path, oracle, pkg, golden_csr):
