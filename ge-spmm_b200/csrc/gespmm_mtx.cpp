@@ -2,9 +2,9 @@
 //
 // Same post-conditions as the reference's readMtx<float> followed by the CLI's COO->CSR
 // (util/util.hpp:286-333, 218-284, 75-102; util/mmio.hpp:215-336; spmm_test.cu:557-581), a
-// different construction: the file is slurped once and tokenised by hand (the reference calls
-// fscanf three times per entry), entries are bucketed by row with a counting sort and each
-// row is then ordered by column (the reference sorts a vector of 4-tuples, O(nnz log nnz)),
+// different construction: the file is slurped once and tokenised by hand on all host threads (the
+// reference calls fscanf three times per entry, single-threaded), entries are bucketed by row with a
+// counting sort and each row is then ordered by column (the reference sorts a vector of 4-tuples, O(nnz log nnz)),
 // and the CSR arrays are produced directly.
 //
 //   general    keep every entry, duplicates and self-loops included        (util.hpp:327)
@@ -16,10 +16,12 @@
 //              (readMtx only tests mm_is_symmetric, util.hpp:323)
 #include <algorithm>
 #include <cctype>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "gespmm.h"
@@ -61,6 +63,17 @@ std::string lower(std::string s) {
     return s;
 }
 
+struct StageTimer {  // GESPMM_MTX_TIMING=1 prints where the reader's time goes
+    bool on = getenv("GESPMM_MTX_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void mark(const char *what) {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[gespmm_read_mtx] %-22s %.3f s\n", what, std::chrono::duration<double>(n - t).count());
+        t = n;
+    }
+};
+
 template <typename T>
 T *dup_to_malloc(const std::vector<T> &v) {
     T *p = (T *)malloc((v.empty() ? 1 : v.size()) * sizeof(T));
@@ -90,6 +103,8 @@ extern "C" int gespmm_read_mtx(const char *path, int32_t *nrows, int32_t *ncols,
         buf.resize(got + 1);
     }
     const char *p = buf.data(), *end = buf.data() + buf.size() - 1;
+    StageTimer timer;
+    timer.mark("read file");
 
     // banner line: five tokens, the first is matched by prefix, the rest case-insensitively
     const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
@@ -118,10 +133,73 @@ extern "C" int gespmm_read_mtx(const char *path, int32_t *nrows, int32_t *ncols,
     }
     if (M < 0 || N < 0 || nz < 0 || M > INT32_MAX - 1 || N > INT32_MAX || nz > INT32_MAX) return GESPMM_ERR_TOO_LARGE;
 
+    // Entries are parsed in parallel: the data section is cut into one slice per thread at line
+    // boundaries, every thread tokenises its slice, and the slices are concatenated in file order
+    // (so duplicates keep their file order, like a sequential read).  A file that is not one
+    // entry per line falls back to the sequential tokeniser below.
     std::vector<int32_t> er, ec;
     std::vector<float> ev;
-    er.reserve((size_t)nz); ec.reserve((size_t)nz); ev.reserve((size_t)nz);
-    if (is_int || is_real || is_pat) {
+    const bool has_entries = is_int || is_real || is_pat;
+    const char *data = p;
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (nthreads == 0) nthreads = 1;
+    if (nthreads > 8) nthreads = 8;
+    if ((size_t)(end - data) < ((size_t)64 << 20)) nthreads = 1;  // below 64 MB one thread is as fast (measured)
+    bool parallel_ok = has_entries && nthreads > 1;
+    if (parallel_ok) {
+        std::vector<const char *> cut(nthreads + 1);
+        cut[0] = data; cut[nthreads] = end;
+        for (unsigned t = 1; t < nthreads; t++) {
+            const char *q = data + (size_t)(end - data) * t / nthreads;
+            const char *nl = (const char *)memchr(q, '\n', (size_t)(end - q));
+            cut[t] = nl ? nl + 1 : end;
+        }
+        struct Part { std::vector<int32_t> r, c; std::vector<float> v; bool bad = false; };
+        std::vector<Part> parts(nthreads);
+        auto work = [&](unsigned t) {
+            Part &pt = parts[t];
+            const char *q = cut[t], *qe = cut[t + 1];
+            const size_t guess = (size_t)(qe - q) / 8 + 16;
+            pt.r.reserve(guess); pt.c.reserve(guess); pt.v.reserve(guess);
+            while (true) {
+                q = skip_ws(q, qe);
+                if (q >= qe) break;
+                const char *le = (const char *)memchr(q, '\n', (size_t)(qe - q));
+                if (!le) le = qe;
+                long long r, c;
+                float v = 1.0f;
+                const char *x = q;
+                if (!parse_int(x, le, r) || !parse_int(x, le, c)) { pt.bad = true; return; }
+                if (is_int) { long long iv = 0; if (!parse_int(x, le, iv)) { pt.bad = true; return; } v = (float)(int)iv; }
+                else if (is_real) { if (!parse_float(x, le, v)) { pt.bad = true; return; } }
+                if (skip_ws(x, le) != le && !is_pat) { pt.bad = true; return; }  // trailing tokens: not one entry per line
+                pt.r.push_back((int32_t)(r - 1)); pt.c.push_back((int32_t)(c - 1)); pt.v.push_back(v);
+                q = le;
+            }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nthreads; t++) pool.emplace_back(work, t);
+        work(0);
+        for (auto &th : pool) th.join();
+        size_t tot = 0;
+        for (auto &pt : parts) { parallel_ok = parallel_ok && !pt.bad; tot += pt.r.size(); }
+        if (parallel_ok) {
+            if (tot > (size_t)nz) tot = (size_t)nz;  // more lines than promised: the reader stops at nz
+            er.resize(tot); ec.resize(tot); ev.resize(tot);
+            size_t off = 0;
+            for (auto &pt : parts) {
+                const size_t k = std::min(pt.r.size(), tot - off);
+                if (k) {
+                    memcpy(er.data() + off, pt.r.data(), k * 4); memcpy(ec.data() + off, pt.c.data(), k * 4);
+                    memcpy(ev.data() + off, pt.v.data(), k * 4);
+                }
+                off += k;
+            }
+        }
+    }
+    if (!parallel_ok && has_entries) {
+        er.reserve((size_t)nz); ec.reserve((size_t)nz); ev.reserve((size_t)nz);
+        p = data;
         for (long long i = 0; i < nz; i++) {
             long long r, c;
             if (!parse_int(p, end, r)) break;  // fewer entries than promised: keep what was read
@@ -132,6 +210,7 @@ extern "C" int gespmm_read_mtx(const char *path, int32_t *nrows, int32_t *ncols,
             er.push_back((int32_t)(r - 1)); ec.push_back((int32_t)(c - 1)); ev.push_back(v);
         }
     }
+    timer.mark("tokenise");
     size_t n = er.size();
     for (size_t i = 0; i < n; i++)
         if (er[i] < 0 || er[i] >= M || ec[i] < 0 || ec[i] >= N) return GESPMM_ERR_IO;
@@ -143,6 +222,7 @@ extern "C" int gespmm_read_mtx(const char *path, int32_t *nrows, int32_t *ncols,
     }
     if (n > (size_t)INT32_MAX) return GESPMM_ERR_TOO_LARGE;
 
+    timer.mark("validate / mirror");
     // bucket by row (stable), order each row by column (stable)
     std::vector<int32_t> rowptr((size_t)M + 1, 0);
     for (size_t i = 0; i < n; i++) rowptr[(size_t)er[i] + 1]++;
@@ -153,12 +233,23 @@ extern "C" int gespmm_read_mtx(const char *path, int32_t *nrows, int32_t *ncols,
         for (size_t i = 0; i < n; i++) ent[(size_t)cursor[er[i]]++] = Entry{ec[i], ev[i]};
     }
     std::vector<int32_t>().swap(er); std::vector<int32_t>().swap(ec); std::vector<float>().swap(ev);
-    for (long long r = 0; r < M; r++) {
-        Entry *b = ent.data() + rowptr[r], *e = ent.data() + rowptr[r + 1];
-        if (e - b > 1 && !std::is_sorted(b, e, [](const Entry &x, const Entry &y) { return x.col < y.col; }))
-            std::stable_sort(b, e, [](const Entry &x, const Entry &y) { return x.col < y.col; });
+    timer.mark("bucket by row");
+    {
+        auto sort_rows = [&](long long r0, long long r1) {
+            for (long long r = r0; r < r1; r++) {
+                Entry *b = ent.data() + rowptr[r], *e = ent.data() + rowptr[r + 1];
+                if (e - b > 1 && !std::is_sorted(b, e, [](const Entry &x, const Entry &y) { return x.col < y.col; }))
+                    std::stable_sort(b, e, [](const Entry &x, const Entry &y) { return x.col < y.col; });
+            }
+        };
+        const unsigned nt = (n > ((size_t)1 << 20)) ? nthreads : 1;
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nt; t++) pool.emplace_back(sort_rows, M * t / nt, M * (t + 1) / nt);
+        sort_rows(0, M / nt);
+        for (auto &th : pool) th.join();
     }
 
+    timer.mark("sort rows");
     std::vector<int32_t> colind;
     std::vector<float> val;
     colind.reserve(n); val.reserve(n);
@@ -179,11 +270,13 @@ extern "C" int gespmm_read_mtx(const char *path, int32_t *nrows, int32_t *ncols,
         for (size_t i = 0; i < n; i++) { colind.push_back(ent[i].col); val.push_back(ent[i].val); }
     }
 
+    timer.mark("compact");
     int32_t *rp = dup_to_malloc(rowptr);
     int32_t *ci = dup_to_malloc(colind);
     float *vv = dup_to_malloc(val);
     if (!rp || !ci || !vv) { free(rp); free(ci); free(vv); return GESPMM_ERR_NOMEM; }
     *nrows = (int32_t)M; *ncols = (int32_t)N; *nnz_out = (int64_t)colind.size();
     *rowptr_out = rp; *colind_out = ci; *val_out = vv;
+    timer.mark("copy out");
     return GESPMM_OK;
 }
