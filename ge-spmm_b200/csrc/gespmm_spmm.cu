@@ -55,6 +55,7 @@
 
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 
@@ -658,9 +659,15 @@ cudaError_t launch(const Args &a)
     if (has_b) {
         constexpr int dynB = WK::kRingBytes * kLongWarps;
         auto kernB = spmm_long_kernel<WK, V, VEC4>;
-        if (dynB > 0) {
-            static cudaError_t attr = cudaFuncSetAttribute(kernB, cudaFuncAttributeMaxDynamicSharedMemorySize, dynB);
-            if (attr != cudaSuccess) return attr;
+        if (dynB > 48 * 1024) {  // opt in to > 48 KB of dynamic shared memory, once per device
+            static bool done[kMaxDevices] = {};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (dev >= 0 && dev < kMaxDevices && !done[dev]) {
+                const cudaError_t e = cudaFuncSetAttribute(kernB, cudaFuncAttributeMaxDynamicSharedMemorySize, dynB);
+                if (e != cudaSuccess) return e;
+                done[dev] = true;
+            }
         }
         cudaStream_t sb = a.st;
         if (sd) {
@@ -764,19 +771,22 @@ extern "C" int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
     const int V = packs >= 4 ? 4 : packs;
     const bool masked = (K % (32 * W * V)) != 0;  // some lanes' packs fall beyond K
 
-    // Task window (keys per task): sized so the grid is ~40 waves of resident CTAs -- small enough
-    // that the tail of the last wave is negligible, large enough (<= 512) that a task's start-up
-    // (row search, first rowptr/colind fetch) is amortised.  Measured on B200: 128 is best for the
-    // 20 M-key cit-Patents shape, 512 for the 100-200 M-key Reddit / products / R-MAT shapes.
-    // GESPMM_TASK / GESPMM_LONG / GESPMM_VARIANT are tuning overrides (read per call).
+    // Task window (keys per task).  A task's start-up (row search, first rowptr / colind fetch) is
+    // amortised over its window, but its rows are walked 32 at a time, so the best window grows with
+    // the average row: measured optima on B200 are ~96 keys at 5 keys/row (cit-Patents shape, at 2.5 M
+    // to 20 M keys), ~256 at 21 (R-MAT), 512-1024 at ~500 (Reddit shape), i.e. ~48*sqrt(keys per row);
+    // capped so that the grid keeps at least ~8 waves of resident CTAs.
+    // GESPMM_TASK / GESPMM_LONG / GESPMM_VARIANT / GESPMM_OVERLAP are tuning overrides (read per call).
     const int forced_task = env_int("GESPMM_TASK", 0);
     const int forced_long = env_int("GESPMM_LONG", 0);
     const int variant = env_int("GESPMM_VARIANT", 0);
     const long long total = nnz + M;
     const long long warps_per_wave = 148LL * 24;
-    long long tk = total / (40 * warps_per_wave);
-    tk &= ~31LL;
-    int task = (int)(tk < 32 ? 32 : (tk > 512 ? 512 : tk));
+    const double keys_per_row = (double)total / (double)M;
+    long long tk = ((long long)(48.0 * sqrt(keys_per_row)) + 31) & ~31LL;
+    const long long cap = (total / (8 * warps_per_wave)) & ~31LL;
+    if (tk > cap) tk = cap;
+    int task = (int)(tk < 32 ? 32 : (tk > kMaxTask ? kMaxTask : tk));
     if (forced_task >= 32 && forced_task <= kMaxTask) task = forced_task & ~31;
     int long_row = GESPMM_LONG_ROW;
     if (forced_long >= kMinLong) long_row = forced_long;
