@@ -659,7 +659,7 @@ cudaError_t launch(const Args &a)
     if (has_b) {
         constexpr int dynB = WK::kRingBytes * kLongWarps;
         auto kernB = spmm_long_kernel<WK, V, VEC4>;
-        if (dynB > 48 * 1024) {  // opt in to > 48 KB of dynamic shared memory, once per device
+        if (dynB > 0) {  // static + dynamic shared memory exceeds the 48 KB default: opt in, once per device
             static bool done[kMaxDevices] = {};
             int dev = 0;
             cudaGetDevice(&dev);
