@@ -244,6 +244,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ref-kernel", action="store_true")
+    ap.add_argument("--b-sharded", action="store_true",
+                    help="N > 1: leave B row-sharded (no replication) and let the kernel gather remote rows over NVLink")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 3
@@ -300,8 +302,20 @@ def main():
         t = torch.zeros(world, 2, device=dev, dtype=torch.int64); t[rank, 0] = M_loc; t[rank, 1] = nnz_loc
         dist.all_reduce(t); per_rank_shape = t.tolist()
 
-    def step():
-        return sh.forward(B)
+    remote_frac = None
+    if args.b_sharded and world > 1:
+        bb = sh.b_row_bounds()
+        parts = sh.share_B_parts(B[bb[rank]:bb[rank + 1]].clone())
+        remote = ((sh.colind < bb[rank]) | (sh.colind >= bb[rank + 1])).sum()
+        t = torch.stack([remote.double(), torch.tensor(float(nnz_loc), device=dev, dtype=torch.float64)])
+        dist.all_reduce(t)
+        remote_frac = float(t[0] / t[1])
+
+        def step():
+            return sh.forward_sharded_B(parts)
+    else:
+        def step():
+            return sh.forward(B)
 
     for _ in range(args.warmup):
         C = step()
@@ -432,6 +446,8 @@ def main():
                    "degree_stats": stats},
         "roofline": roofline, "e2e": e2e, "gpu_launches": args.steps * (2 if nnz_loc > 4096 else 1), "clocks": clocks,
         "b_broadcast_ms": bcast_ms if world > 1 else None, "per_rank_ms": per_rank_ms,
+        "b_layout": ("row-sharded, remote rows gathered over NVLink inside the kernel (no replication); fraction of gathers "
+                     "that are remote: %.3f" % remote_frac) if remote_frac is not None else "replicated on every rank",
         "per_rank_rows_nnz": per_rank_shape,
     }
 

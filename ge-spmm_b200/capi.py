@@ -18,7 +18,7 @@ LONG_ROW = 4096
 
 # every symbol include/gespmm.h declares
 SYMBOLS = (
-    "gespmm_version", "gespmm_error_string", "gespmm_csr_spmm_f32", "gespmm_csr_spmm_f32_host",
+    "gespmm_version", "gespmm_error_string", "gespmm_csr_spmm_f32", "gespmm_csr_spmm_f32_host", "gespmm_csr_spmm_f32_bparts",
     "gespmm_csr2csc_workspace_bytes", "gespmm_csr2csc_f32", "gespmm_read_mtx", "gespmm_free_host",
 )
 
@@ -46,6 +46,9 @@ def lib():
         L.gespmm_error_string.argtypes = [ctypes.c_int]
         L.gespmm_csr_spmm_f32.restype = ctypes.c_int
         L.gespmm_csr_spmm_f32.argtypes = [i64, i64, i64, i64, p, p, p, p, i64, p, i64, p]
+        L.gespmm_csr_spmm_f32_bparts.restype = ctypes.c_int
+        L.gespmm_csr_spmm_f32_bparts.argtypes = [i64, i64, i64, i64, p, p, p, ctypes.c_int, ctypes.POINTER(p),
+                                                 ctypes.POINTER(i64), i64, p, i64, p]
         L.gespmm_csr_spmm_f32_host.restype = ctypes.c_int
         L.gespmm_csr_spmm_f32_host.argtypes = [i64, i64, i64, i64, p, p, p, p, i64, p, i64, ctypes.c_int]
         L.gespmm_csr2csc_workspace_bytes.restype = sz
@@ -75,6 +78,17 @@ def csr_spmm_f32(M, N, K, nnz, rowptr, colind, val, B, ldb, C, ldc, stream=None)
     rc = lib().gespmm_csr_spmm_f32(M, N, K, nnz, rowptr, colind, val or None, B, ldb, C, ldc, stream or None)
     if rc != OK:
         raise GespmmError(rc, "gespmm_csr_spmm_f32")
+
+
+def csr_spmm_f32_bparts(M, N, K, nnz, rowptr, colind, val, part_ptrs, part_begin, ldb, C, ldc, stream=None):
+    """B as row blocks: ``part_ptrs`` device pointers (ints), ``part_begin`` row boundaries (len parts + 1)."""
+    parts = len(part_ptrs)
+    ptrs = (ctypes.c_void_p * parts)(*[ctypes.c_void_p(int(x)) for x in part_ptrs])
+    begins = (ctypes.c_int64 * (parts + 1))(*[int(x) for x in part_begin])
+    rc = lib().gespmm_csr_spmm_f32_bparts(M, N, K, nnz, rowptr, colind, val or None, parts, ptrs, begins, ldb, C, ldc,
+                                          stream or None)
+    if rc != OK:
+        raise GespmmError(rc, "gespmm_csr_spmm_f32_bparts")
 
 
 def csr_spmm_host(rowptr, colind, val, B, device=0):

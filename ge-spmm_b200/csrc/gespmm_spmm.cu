@@ -59,6 +59,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "gespmm.h"
 
 namespace {
@@ -130,12 +132,23 @@ __device__ __forceinline__ int search_key16(const int *__restrict__ rowptr, int 
     return lo;
 }
 
+constexpr int kMaxParts = 8;  // row blocks of a sharded B (one per GPU of an NVLink domain)
+
+// B given as row blocks that live in different allocations -- typically one per GPU, mapped into this
+// process through CUDA IPC and read over NVLink: block q holds rows [lo[q], lo[q+1]) at base[q].
+struct PeerMap {
+    const float *base[kMaxParts];
+    int lo[kMaxParts + 1];
+    int parts;  // 0: B is one array (Operands::B)
+};
+
 struct Operands {
     const int *colind;
     const float *val;
     const float *B;
     float *C;
     int ldb, ldc;
+    PeerMap peer;
 };
 
 // =================================================================================================
@@ -258,8 +271,11 @@ __device__ __forceinline__ float4 lds128(unsigned saddr)
 // G rows per stage, NS stages (power of two, divides S32 = 32/G).  Stage j of a 32-nonzero chunk
 // lives in ring slot j % NS; the copies for stage j + NS - 1 are issued right before stage j is
 // consumed.  MASKED: some lanes' packs lie beyond K (K is not a multiple of 128*V).
-template <int V, bool VALUED, int G, int NS, int CP, bool MASKED>
+template <int V, bool VALUED, int G, int NS, int CP, bool MASKED, bool PEER = false>
 struct WalkerRing {
+    // what a lane keeps per prefetched nonzero: its column (B is one array) or the byte address of its
+    // B row (B is a set of row blocks; the owner lookup is done once, by the lane that loaded the column)
+    using Tok = typename std::conditional<PEER, unsigned long long, int>::type;
     using P = Pack<true>;
     using T = float4;
     static constexpr int kStride = 128;
@@ -279,11 +295,27 @@ struct WalkerRing {
     unsigned vmask;
     int lane;
     unsigned ring;              // shared-space address of this lane's 16 bytes in (slot 0, row 0, pack 0)
+    const PeerMap *peer;        // PEER: the row blocks of B (in the kernel's parameter space)
+    unsigned lane_off;          // PEER: byte offset of this lane's first owned column inside a B row
 
     __device__ __forceinline__ void init(const Operands &o, int col0, unsigned vm, int ln, unsigned ring_base) {
         colind = o.colind; val = o.val; Bl = reinterpret_cast<const char *>(o.B + col0); Cl = o.C + col0;
         ldb_bytes = (unsigned)o.ldb * 4u; ldc = o.ldc; vmask = vm; lane = ln;
         ring = ring_base + ln * 16;
+        peer = &o.peer; lane_off = (unsigned)col0 * 4u;
+    }
+
+    __device__ __forceinline__ Tok load_tok(int p) const {
+        const int c = __ldcs(colind + p);
+        if constexpr (PEER) {
+            int q = 0;
+#pragma unroll
+            for (int i = 1; i < kMaxParts; i++) q += (i < peer->parts && c >= peer->lo[i]) ? 1 : 0;
+            return (unsigned long long)reinterpret_cast<uintptr_t>(peer->base[q]) +
+                   (unsigned long long)(unsigned)(c - peer->lo[q]) * ldb_bytes;
+        } else {
+            return c;
+        }
     }
 
     __device__ __forceinline__ bool pack_on(int v) const { return !MASKED || (vmask & (1u << v)); }
@@ -298,7 +330,7 @@ struct WalkerRing {
     // copies for the G nonzeros at chunk positions [pos0, pos0 + G) of a chunk holding n nonzeros,
     // into the stage at byte offset `slot` of the ring; always exactly one commit group
     template <bool FULL>
-    __device__ __forceinline__ void issue_impl(int cols, int pos0, int n, unsigned slot) const {
+    __device__ __forceinline__ void issue_impl(Tok cols, int pos0, int n, unsigned slot) const {
         // addresses first, then the copies back to back (ptxas pads every LDGSTS that follows other
         // work with three dummy LDS; consecutive LDGSTS share one such pad)
 #pragma unroll
@@ -306,8 +338,9 @@ struct WalkerRing {
             const char *bp[UB];
 #pragma unroll
             for (int i = 0; i < UB; i++) {
-                const unsigned c = (unsigned)__shfl_sync(kFull, cols, pos0 + i0 + i);
-                bp[i] = Bl + (unsigned long long)c * ldb_bytes;
+                const Tok t = __shfl_sync(kFull, cols, pos0 + i0 + i);
+                if constexpr (PEER) bp[i] = reinterpret_cast<const char *>((uintptr_t)(t + lane_off));
+                else bp[i] = Bl + (unsigned long long)(unsigned)t * ldb_bytes;
             }
 #pragma unroll
             for (int i = 0; i < UB; i++) {
@@ -320,7 +353,7 @@ struct WalkerRing {
         }
         cp_async_commit();
     }
-    __device__ __forceinline__ void issue(int cols, int pos0, int n, unsigned slot) const {
+    __device__ __forceinline__ void issue(Tok cols, int pos0, int n, unsigned slot) const {
         if (pos0 + G <= n) issue_impl<true>(cols, pos0, n, slot);
         else issue_impl<false>(cols, pos0, n, slot);
     }
@@ -380,20 +413,20 @@ struct WalkerRing {
     }
 
     __device__ __forceinline__ void stream(int s, int e, T (&acc)[V], int my_end, unsigned rows, int rb) const {
-        int ccol = 0, ncol = 0, fcol = 0;
+        Tok ccol = 0, ncol = 0, fcol = 0;
         float cval = 1.f, nval = 1.f;
         if (s + lane < e) {
-            ccol = __ldcs(colind + s + lane);
+            ccol = load_tok(s + lane);
             if (VALUED) cval = __ldcs(val + s + lane);
         }
-        if (s + 32 + lane < e) ncol = __ldcs(colind + s + 32 + lane);
+        if (s + 32 + lane < e) ncol = load_tok(s + 32 + lane);
         const bool my_row = (rows >> lane) & 1u;
         unsigned rows_left = rows;
 #pragma unroll
         for (int j = 0; j < L; j++) issue(ccol, j * G, min(32, e - s), (j % NS) * kStageBytes);
 #pragma unroll 1
         for (int p0 = s; p0 < e; p0 += 32) {
-            if (p0 + 64 + lane < e) fcol = __ldcs(colind + p0 + 64 + lane);
+            if (p0 + 64 + lane < e) fcol = load_tok(p0 + 64 + lane);
             if (VALUED && p0 + 32 + lane < e) nval = __ldcs(val + p0 + 32 + lane);
             const unsigned rel = (unsigned)(my_end - 1 - p0);
             const unsigned endmask = __reduce_or_sync(kFull, (my_row && rel < 32u) ? (1u << rel) : 0u);
@@ -700,6 +733,15 @@ cudaError_t launch_ring(const Args &a, bool masked)
                   : launch<WalkerRing<V, VALUED, G, NS, CP, false>, V, true, MINB>(a);
 }
 
+template <int V, bool VALUED>
+cudaError_t launch_peer(const Args &a, bool masked)
+{
+    constexpr int G = V == 1 ? 8 : (V == 2 ? 4 : 2);
+    constexpr int MINB = V == 1 ? 24 : (V == 2 ? 20 : (V == 3 ? 24 : 16));
+    return masked ? launch<WalkerRing<V, VALUED, G, 2, 0, true, true>, V, true, MINB>(a)
+                  : launch<WalkerRing<V, VALUED, G, 2, 0, false, true>, V, true, MINB>(a);
+}
+
 int env_int(const char *name, int dflt)
 {
     const char *s = getenv(name);
@@ -752,9 +794,12 @@ cudaError_t launch_v(int V, int variant, bool masked, const Args &a)
 
 }  // namespace
 
-extern "C" int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr,
-                                   const int32_t *colind, const float *val, const float *B, int64_t ldb,
-                                   float *C, int64_t ldc, void *stream)
+namespace {
+
+// Shared by the two entry points: argument checks, task window, dispatch.  `parts` == 0: B is one array.
+int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr, const int32_t *colind, const float *val,
+             const float *B, int parts, const float *const *B_parts, const int64_t *part_begin, int64_t ldb, float *C,
+             int64_t ldc, void *stream)
 {
     if (M < 0 || N < 0 || K < 0 || nnz < 0) return GESPMM_ERR_INVALID_ARG;
     if (M > INT32_MAX - 64 || N > INT32_MAX || nnz > INT32_MAX - 64 || K > INT32_MAX || ldb >= (1LL << 30) || ldc > INT32_MAX)
@@ -762,10 +807,29 @@ extern "C" int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
     if (M == 0 || K == 0) return GESPMM_OK;
     if (ldb < K || ldc < K) return GESPMM_ERR_INVALID_ARG;
     if (!rowptr || !C) return GESPMM_ERR_INVALID_ARG;
-    if (nnz > 0 && (!colind || !B)) return GESPMM_ERR_INVALID_ARG;
+    if (nnz > 0 && !colind) return GESPMM_ERR_INVALID_ARG;
+    if (parts == 0 && nnz > 0 && !B) return GESPMM_ERR_INVALID_ARG;
 
-    const bool vec4 = (K % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) &&
-                      ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    bool vec4 = (K % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    Args a;
+    a.op.peer.parts = 0;
+    if (parts > 0) {
+        if (parts > kMaxParts || !B_parts || !part_begin) return GESPMM_ERR_INVALID_ARG;
+        if (part_begin[0] != 0 || part_begin[parts] != N) return GESPMM_ERR_INVALID_ARG;
+        for (int q = 0; q < parts; q++) {
+            if (part_begin[q + 1] < part_begin[q]) return GESPMM_ERR_INVALID_ARG;
+            if (part_begin[q + 1] > part_begin[q] && !B_parts[q]) return GESPMM_ERR_INVALID_ARG;
+            if (reinterpret_cast<uintptr_t>(B_parts[q]) & 15) return GESPMM_ERR_INVALID_ARG;  // the sharded path is the aligned path
+            a.op.peer.base[q] = B_parts[q];
+            a.op.peer.lo[q] = (int)part_begin[q];
+        }
+        for (int q = parts; q < kMaxParts; q++) a.op.peer.base[q] = nullptr;
+        for (int q = parts; q <= kMaxParts; q++) a.op.peer.lo[q] = (int)N;
+        a.op.peer.parts = parts;
+        if (!vec4) return GESPMM_ERR_INVALID_ARG;  // needs K % 4 == 0 and 16-byte aligned, 4-float-strided operands
+    } else {
+        vec4 = vec4 && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+    }
     const int W = vec4 ? 4 : 1;
     const int packs = (int)((K + 32 * W - 1) / (32 * W));
     const int V = packs >= 4 ? 4 : packs;
@@ -791,13 +855,39 @@ extern "C" int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
     int long_row = GESPMM_LONG_ROW;
     if (forced_long >= kMinLong) long_row = forced_long;
 
-    Args a;
     a.M = (int)M; a.K = (int)K; a.task = task; a.long_row = long_row; a.nnz = nnz; a.rowptr = rowptr;
     a.op.colind = colind; a.op.val = val; a.op.B = B; a.op.C = C; a.op.ldb = (int)ldb; a.op.ldc = (int)ldc;
     a.st = static_cast<cudaStream_t>(stream);
     a.overlap = env_int("GESPMM_OVERLAP", 1) != 0;
     cudaError_t err;
-    if (val) err = vec4 ? launch_v<true, true>(V, variant, masked, a) : launch_v<true, false>(V, variant, masked, a);
-    else err = vec4 ? launch_v<false, true>(V, variant, masked, a) : launch_v<false, false>(V, variant, masked, a);
+    if (parts > 0) {
+        switch (V) {
+            case 1: err = val ? launch_peer<1, true>(a, masked) : launch_peer<1, false>(a, masked); break;
+            case 2: err = val ? launch_peer<2, true>(a, masked) : launch_peer<2, false>(a, masked); break;
+            case 3: err = val ? launch_peer<3, true>(a, masked) : launch_peer<3, false>(a, masked); break;
+            default: err = val ? launch_peer<4, true>(a, masked) : launch_peer<4, false>(a, masked); break;
+        }
+    } else if (val) {
+        err = vec4 ? launch_v<true, true>(V, variant, masked, a) : launch_v<true, false>(V, variant, masked, a);
+    } else {
+        err = vec4 ? launch_v<false, true>(V, variant, masked, a) : launch_v<false, false>(V, variant, masked, a);
+    }
     return err == cudaSuccess ? GESPMM_OK : GESPMM_ERR_CUDA;
+}
+
+}  // namespace
+
+extern "C" int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr,
+                                   const int32_t *colind, const float *val, const float *B, int64_t ldb,
+                                   float *C, int64_t ldc, void *stream)
+{
+    return run_spmm(M, N, K, nnz, rowptr, colind, val, B, 0, nullptr, nullptr, ldb, C, ldc, stream);
+}
+
+extern "C" int gespmm_csr_spmm_f32_bparts(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr,
+                                          const int32_t *colind, const float *val, int parts, const float *const *B_parts,
+                                          const int64_t *part_begin, int64_t ldb, float *C, int64_t ldc, void *stream)
+{
+    if (parts < 1) return GESPMM_ERR_INVALID_ARG;
+    return run_spmm(M, N, K, nnz, rowptr, colind, val, nullptr, parts, B_parts, part_begin, ldb, C, ldc, stream);
 }

@@ -114,6 +114,41 @@ class RowShardedSpMM:
         """C[row_lo:row_hi, :] for this rank."""
         return self.spmm_fn(self.rowptr, self.colind, self.val, B_full)
 
+    # -- no replication: B stays row-sharded, the kernel gathers remote rows over NVLink -------------
+    def share_B_parts(self, B_local):
+        """Exchange CUDA IPC handles of every rank's row block of B (rows b_row_bounds()[p] .. [p+1]).
+        Returns the list of blocks as tensors: this rank's own tensor and peer-mapped views of the others
+        (torch opens the handles with lazy peer access, so kernels on this device can read them over
+        NVLink).  The owners must keep their blocks alive while the views are in use."""
+        if self.world == 1:
+            return [B_local]
+        from torch.multiprocessing.reductions import reduce_tensor
+        B_local = B_local.contiguous()
+        payload = [None] * self.world
+        dist.all_gather_object(payload, reduce_tensor(B_local), group=self.group)
+        parts = []
+        for q, (rebuild, args) in enumerate(payload):
+            parts.append(B_local if q == self.rank else rebuild(*args))
+        self._ipc_owner = B_local  # keep our exported block alive
+        return parts
+
+    def forward_sharded_B(self, parts, stream=None):
+        """C[row_lo:row_hi, :] = A[row block] @ B with B given as row blocks (see share_B_parts): one fused
+        kernel computes and pulls the remote B rows over NVLink; nothing is replicated."""
+        from . import capi
+        bb = self.b_row_bounds()
+        K = next(p.shape[1] for p in parts if p.shape[0] > 0)
+        M_loc = self.row_hi - self.row_lo
+        C = torch.empty(M_loc, K, dtype=torch.float32, device=self.device)
+        for q, p in enumerate(parts):
+            assert p.dtype == torch.float32 and p.is_contiguous() and p.shape[0] == bb[q + 1] - bb[q]
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        with torch.cuda.device(self.device):
+            capi.csr_spmm_f32_bparts(M_loc, self.N, K, self.nnz_local, self.rowptr.data_ptr(), self.colind.data_ptr(),
+                                     None if self.val is None else self.val.data_ptr(),
+                                     [p.data_ptr() if p.shape[0] else 0 for p in parts], bb, K, C.data_ptr(), K, st)
+        return C
+
     def gather_C(self, C_local, dst=0):
         """Assemble the full C on ``dst`` (tests / validation only; the product leaves C sharded)."""
         K = C_local.shape[1]

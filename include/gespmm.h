@@ -76,6 +76,21 @@ int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
                         const int32_t *rowptr, const int32_t *colind, const float *val,
                         const float *B, int64_t ldb, float *C, int64_t ldc, void *stream);
 
+/*
+ * Same product with B given as `parts` (<= 8) row blocks that live in different allocations: block q
+ * holds rows [part_begin[q], part_begin[q+1]) of B, row-major with stride ldb, at B_parts[q]
+ * (part_begin[0] == 0, part_begin[parts] == N).  B_parts and part_begin are HOST arrays of `parts` and
+ * `parts + 1` entries; the pointers in B_parts are device pointers readable from the current device --
+ * in the multi-GPU use they are the other ranks' row blocks of B, mapped through CUDA IPC, and the
+ * kernel gathers their rows over NVLink while it computes: there is no replication step and no
+ * replicated copy of B.  (New: the reference is single-GPU; its B is one array.)
+ * Requires K % 4 == 0, ldb % 4 == 0, ldc % 4 == 0 and 16-byte aligned blocks and C.
+ */
+int gespmm_csr_spmm_f32_bparts(int64_t M, int64_t N, int64_t K, int64_t nnz,
+                               const int32_t *rowptr, const int32_t *colind, const float *val,
+                               int parts, const float *const *B_parts, const int64_t *part_begin,
+                               int64_t ldb, float *C, int64_t ldc, void *stream);
+
 /* Rows with more nonzeros than this take the segmented path described above. */
 #define GESPMM_LONG_ROW 4096
 

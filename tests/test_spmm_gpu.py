@@ -212,6 +212,37 @@ def test_c_abi_strides_alignment_and_stream(dev, oracle, pkg):
         assert torch.isnan(Cview[:, K:]).all(), "padding columns of C must not be written"
 
 
+@pytest.mark.parametrize("K", [128, 64, 200, 512])
+def test_c_abi_b_given_as_row_blocks(dev, oracle, pkg, K):
+    """gespmm_csr_spmm_f32_bparts: B split into separately allocated row blocks (here all on one device; across
+    GPUs in test_sharding_nccl_gpu.py) gives the same bits as one contiguous B, long and huge rows included."""
+    from gespmm_b200 import capi
+    rng = np.random.default_rng(31 + K)
+    M, N = 900, 4000
+    deg = rng.integers(0, 10, M); deg[[3, 500]] = [40000, 6000]
+    rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    nnz = int(rowptr[-1])
+    colind = rng.integers(0, N, nnz).astype(np.int32)
+    val = rng.standard_normal(nnz).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32)
+    rp, ci, v, Bd = (torch.as_tensor(x, device=dev) for x in (rowptr, colind, val, B))
+    for bounds in ([0, N], [0, 1000, 1000, 2500, N], [0, 1, 2, 3, 4, 5, 6, 7, N]):
+        parts = [Bd[a:b].clone() for a, b in zip(bounds[:-1], bounds[1:])]
+        for vv in (None, v):
+            C = torch.full((M, K), float("nan"), device=dev)
+            capi.csr_spmm_f32_bparts(M, N, K, nnz, rp.data_ptr(), ci.data_ptr(), None if vv is None else vv.data_ptr(),
+                                     [p.data_ptr() if p.shape[0] else 0 for p in parts], bounds, K, C.data_ptr(), K,
+                                     torch.cuda.current_stream().cuda_stream)
+            whole = torch.empty(M, K, device=dev)
+            capi.csr_spmm_f32(M, N, K, nnz, rp.data_ptr(), ci.data_ptr(), None if vv is None else vv.data_ptr(), Bd.data_ptr(), K,
+                              whole.data_ptr(), K, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert torch.equal(C, whole), (K, bounds)
+            _check(oracle, rowptr, colind, None if vv is None else val, B, C)
+    with pytest.raises(capi.GespmmError):  # blocks must cover [0, N)
+        capi.csr_spmm_f32_bparts(M, N, K, nnz, rp.data_ptr(), ci.data_ptr(), None, [Bd.data_ptr()], [0, N - 1], K, C.data_ptr(), K)
+
+
 def test_c_abi_host_buffers(oracle, pkg):
     from gespmm_b200 import capi
     rng = np.random.default_rng(10)
