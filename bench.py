@@ -312,7 +312,7 @@ def main():
         remote_frac = float(t[0] / t[1])
 
         def step():
-            return sh.forward_sharded_B(parts)
+            return sh.forward_sharded_B(parts, K)
     else:
         def step():
             return sh.forward(B)

@@ -18,7 +18,7 @@ LONG_ROW = 4096
 
 # every symbol include/gespmm.h declares
 SYMBOLS = (
-    "gespmm_version", "gespmm_error_string", "gespmm_csr_spmm_f32", "gespmm_csr_spmm_f32_host", "gespmm_csr_spmm_f32_bparts",
+    "gespmm_version", "gespmm_error_string", "gespmm_csr_spmm_f32", "gespmm_csr_spmm_f32_host", "gespmm_csr_spmm_f32_bparts", "gespmm_enable_peer_access", "gespmm_ipc_open", "gespmm_ipc_close", "gespmm_ipc_alloc", "gespmm_ipc_free",
     "gespmm_csr2csc_workspace_bytes", "gespmm_csr2csc_f32", "gespmm_read_mtx", "gespmm_free_host",
 )
 
@@ -49,6 +49,16 @@ def lib():
         L.gespmm_csr_spmm_f32_bparts.restype = ctypes.c_int
         L.gespmm_csr_spmm_f32_bparts.argtypes = [i64, i64, i64, i64, p, p, p, ctypes.c_int, ctypes.POINTER(p),
                                                  ctypes.POINTER(i64), i64, p, i64, p]
+        L.gespmm_enable_peer_access.restype = ctypes.c_int
+        L.gespmm_enable_peer_access.argtypes = [ctypes.c_int]
+        L.gespmm_ipc_open.restype = ctypes.c_int
+        L.gespmm_ipc_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(p)]
+        L.gespmm_ipc_close.restype = ctypes.c_int
+        L.gespmm_ipc_close.argtypes = [p]
+        L.gespmm_ipc_alloc.restype = ctypes.c_int
+        L.gespmm_ipc_alloc.argtypes = [sz, ctypes.POINTER(p), ctypes.c_char_p]
+        L.gespmm_ipc_free.restype = ctypes.c_int
+        L.gespmm_ipc_free.argtypes = [p]
         L.gespmm_csr_spmm_f32_host.restype = ctypes.c_int
         L.gespmm_csr_spmm_f32_host.argtypes = [i64, i64, i64, i64, p, p, p, p, i64, p, i64, ctypes.c_int]
         L.gespmm_csr2csc_workspace_bytes.restype = sz
@@ -78,6 +88,39 @@ def csr_spmm_f32(M, N, K, nnz, rowptr, colind, val, B, ldb, C, ldc, stream=None)
     rc = lib().gespmm_csr_spmm_f32(M, N, K, nnz, rowptr, colind, val or None, B, ldb, C, ldc, stream or None)
     if rc != OK:
         raise GespmmError(rc, "gespmm_csr_spmm_f32")
+
+
+def enable_peer_access(peer_device):
+    rc = lib().gespmm_enable_peer_access(int(peer_device))
+    if rc != OK:
+        raise GespmmError(rc, "gespmm_enable_peer_access(%d)" % peer_device)
+
+
+def ipc_open(handle):
+    """64-byte CUDA IPC memory handle -> base address (int) of the mapping on the current device."""
+    base = ctypes.c_void_p()
+    rc = lib().gespmm_ipc_open(bytes(handle), ctypes.byref(base))
+    if rc != OK:
+        raise GespmmError(rc, "gespmm_ipc_open")
+    return int(base.value)
+
+
+def ipc_alloc(nbytes):
+    """cudaMalloc on the current device -> (device address, 64-byte IPC handle)."""
+    ptr = ctypes.c_void_p()
+    handle = ctypes.create_string_buffer(64)
+    rc = lib().gespmm_ipc_alloc(int(nbytes), ctypes.byref(ptr), handle)
+    if rc != OK:
+        raise GespmmError(rc, "gespmm_ipc_alloc")
+    return int(ptr.value), handle.raw
+
+
+def ipc_free(ptr):
+    lib().gespmm_ipc_free(ctypes.c_void_p(int(ptr)))
+
+
+def ipc_close(base):
+    lib().gespmm_ipc_close(ctypes.c_void_p(int(base)))
 
 
 def csr_spmm_f32_bparts(M, N, K, nnz, rowptr, colind, val, part_ptrs, part_begin, ldb, C, ldc, stream=None):

@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "gespmm.h"
 
@@ -22,6 +23,58 @@ extern "C" const char *gespmm_error_string(int code)
 }
 
 extern "C" void gespmm_free_host(void *p) { free(p); }
+
+// Let kernels on the current device read memory of `peer_device` (NVLink / PCIe P2P).  Needed before
+// gespmm_csr_spmm_f32_bparts is given blocks of B that live on other GPUs.
+extern "C" int gespmm_enable_peer_access(int peer_device)
+{
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) return GESPMM_ERR_CUDA;
+    if (peer_device == cur) return GESPMM_OK;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, cur, peer_device) != cudaSuccess || !can) { cudaGetLastError(); return GESPMM_ERR_CUDA; }
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return GESPMM_OK; }
+    return e == cudaSuccess ? GESPMM_OK : GESPMM_ERR_CUDA;
+}
+
+// Map another process's device allocation (cudaIpcMemHandle_t, 64 bytes) into this process for kernels
+// on the CURRENT device; peer access to the owning GPU is enabled as part of the mapping.
+extern "C" int gespmm_ipc_open(const unsigned char *handle64, void **base)
+{
+    if (!handle64 || !base) return GESPMM_ERR_INVALID_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    *base = nullptr;
+    if (cudaIpcOpenMemHandle(base, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return GESPMM_ERR_CUDA; }
+    return GESPMM_OK;
+}
+
+// A device allocation that other processes can map: plain cudaMalloc (framework caching allocators may
+// hand out virtual-memory segments that cudaIpc* cannot export) plus its 64-byte IPC handle.
+extern "C" int gespmm_ipc_alloc(size_t bytes, void **dptr, unsigned char *handle64)
+{
+    if (!dptr || !handle64) return GESPMM_ERR_INVALID_ARG;
+    *dptr = nullptr;
+    if (cudaMalloc(dptr, bytes ? bytes : 16) != cudaSuccess) { cudaGetLastError(); return GESPMM_ERR_CUDA; }
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, *dptr) != cudaSuccess) { cudaGetLastError(); cudaFree(*dptr); *dptr = nullptr; return GESPMM_ERR_CUDA; }
+    memcpy(handle64, &h, sizeof(h));
+    return GESPMM_OK;
+}
+
+extern "C" int gespmm_ipc_free(void *dptr)
+{
+    if (dptr && cudaFree(dptr) != cudaSuccess) { cudaGetLastError(); return GESPMM_ERR_CUDA; }
+    return GESPMM_OK;
+}
+
+extern "C" int gespmm_ipc_close(void *base)
+{
+    if (!base) return GESPMM_OK;
+    if (cudaIpcCloseMemHandle(base) != cudaSuccess) { cudaGetLastError(); return GESPMM_ERR_CUDA; }
+    return GESPMM_OK;
+}
 
 // Host-buffer convenience call: what the reference CLI does by hand around its launches
 // (cudaMalloc x5 + cudaMemcpy H2D, spmm_test.cu:609-640; D2H under VALIDATE, :689).

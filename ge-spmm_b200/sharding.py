@@ -116,37 +116,66 @@ class RowShardedSpMM:
 
     # -- no replication: B stays row-sharded, the kernel gathers remote rows over NVLink -------------
     def share_B_parts(self, B_local):
-        """Exchange CUDA IPC handles of every rank's row block of B (rows b_row_bounds()[p] .. [p+1]).
-        Returns the list of blocks as tensors: this rank's own tensor and peer-mapped views of the others
-        (torch opens the handles with lazy peer access, so kernels on this device can read them over
-        NVLink).  The owners must keep their blocks alive while the views are in use."""
-        if self.world == 1:
-            return [B_local]
-        from torch.multiprocessing.reductions import reduce_tensor
+        """Put this rank's row block of B (rows b_row_bounds()[p] .. [p+1]) into an exportable device
+        allocation, exchange the CUDA IPC handles, and map the other ranks' blocks for kernels on this device
+        (peer access over NVLink is enabled by the mapping).  Returns the blocks' device addresses (ints),
+        index = owner rank; valid until release_B_parts()."""
+        from . import capi
         B_local = B_local.contiguous()
-        payload = [None] * self.world
-        dist.all_gather_object(payload, reduce_tensor(B_local), group=self.group)
-        parts = []
-        for q, (rebuild, args) in enumerate(payload):
-            parts.append(B_local if q == self.rank else rebuild(*args))
-        self._ipc_owner = B_local  # keep our exported block alive
-        return parts
+        if self.world == 1:
+            self._parts_keep = (B_local, None, [])
+            return [B_local.data_ptr()]
+        with torch.cuda.device(self.device):
+            # torch's allocator may hand out virtual-memory segments that cudaIpc* cannot export: own cudaMalloc
+            own, handle = capi.ipc_alloc(B_local.numel() * 4)
+            holder = type("CudaBuf", (), {})()
+            holder.__cuda_array_interface__ = {"shape": tuple(B_local.shape), "typestr": "<f4", "data": (own, False), "version": 2}
+            block = torch.as_tensor(holder, device=self.device) if B_local.numel() else B_local
+            if B_local.numel():
+                block.copy_(B_local)
+            torch.cuda.synchronize(self.device)
+            payload = [None] * self.world
+            dist.all_gather_object(payload, handle, group=self.group)
+            ptrs, opened = [], []
+            for q, h in enumerate(payload):
+                if q == self.rank:
+                    ptrs.append(own)
+                else:
+                    opened.append(capi.ipc_open(h))
+                    ptrs.append(opened[-1])
+        self._parts_keep = (block, own, opened)
+        dist.barrier(group=self.group)
+        return ptrs
 
-    def forward_sharded_B(self, parts, stream=None):
+    def release_B_parts(self):
+        from . import capi
+        keep = getattr(self, "_parts_keep", None)
+        if keep:
+            torch.cuda.synchronize(self.device)
+            if self.world > 1:
+                dist.barrier(group=self.group)  # nobody unmaps while a peer may still be reading
+            with torch.cuda.device(self.device):
+                for base in keep[2]:
+                    capi.ipc_close(base)
+                if self.world > 1:
+                    dist.barrier(group=self.group)  # every peer has unmapped before the owner frees
+                if keep[1]:
+                    capi.ipc_free(keep[1])
+            self._parts_keep = None
+
+    def forward_sharded_B(self, part_ptrs, K, stream=None):
         """C[row_lo:row_hi, :] = A[row block] @ B with B given as row blocks (see share_B_parts): one fused
         kernel computes and pulls the remote B rows over NVLink; nothing is replicated."""
         from . import capi
         bb = self.b_row_bounds()
-        K = next(p.shape[1] for p in parts if p.shape[0] > 0)
         M_loc = self.row_hi - self.row_lo
         C = torch.empty(M_loc, K, dtype=torch.float32, device=self.device)
-        for q, p in enumerate(parts):
-            assert p.dtype == torch.float32 and p.is_contiguous() and p.shape[0] == bb[q + 1] - bb[q]
         st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
         with torch.cuda.device(self.device):
             capi.csr_spmm_f32_bparts(M_loc, self.N, K, self.nnz_local, self.rowptr.data_ptr(), self.colind.data_ptr(),
                                      None if self.val is None else self.val.data_ptr(),
-                                     [p.data_ptr() if p.shape[0] else 0 for p in parts], bb, K, C.data_ptr(), K, st)
+                                     [p if bb[q + 1] > bb[q] else 0 for q, p in enumerate(part_ptrs)], bb, K,
+                                     C.data_ptr(), K, st)
         return C
 
     def gather_C(self, C_local, dst=0):

@@ -91,6 +91,21 @@ int gespmm_csr_spmm_f32_bparts(int64_t M, int64_t N, int64_t K, int64_t nnz,
                                int parts, const float *const *B_parts, const int64_t *part_begin,
                                int64_t ldb, float *C, int64_t ldc, void *stream);
 
+/* Enable reads of `peer_device`'s memory from kernels on the current device (idempotent). */
+int gespmm_enable_peer_access(int peer_device);
+
+/*
+ * Map a device allocation exported by another process (a 64-byte cudaIpcMemHandle_t from
+ * gespmm_ipc_alloc / cudaIpcGetMemHandle) for kernels on the current device; peer access
+ * to the owning GPU is enabled by the mapping.  *base receives the address of the START of the exported
+ * allocation.  gespmm_ipc_close unmaps it.
+ */
+int gespmm_ipc_open(const unsigned char *handle64, void **base);
+int gespmm_ipc_close(void *base);
+/* cudaMalloc'ed block on the current device plus its IPC handle (what a rank exports of its B block). */
+int gespmm_ipc_alloc(size_t bytes, void **dptr, unsigned char *handle64);
+int gespmm_ipc_free(void *dptr);
+
 /* Rows with more nonzeros than this take the segmented path described above. */
 #define GESPMM_LONG_ROW 4096
 

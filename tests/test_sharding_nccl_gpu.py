@@ -47,11 +47,10 @@ def _worker(rank, world, port, out_dir):
         # B left row-sharded: blocks exchanged as CUDA IPC handles, remote rows gathered over NVLink by the kernel
         mine = B[bb[rank]:bb[rank + 1]].clone()
         parts = sh.share_B_parts(mine)
-        C_fused = sh.forward_sharded_B(parts)
+        C_fused = sh.forward_sharded_B(parts, K)
         torch.cuda.synchronize()
         assert torch.equal(C_fused, C_local), "sharded-B fused product must equal the replicated-B product bit for bit"
-        dist.barrier()
-        del parts
+        sh.release_B_parts()
         full = sh.gather_C(C_local, dst=0)
         if rank == 0:
             want = oracle.spmm(rowptr.numpy(), colind.numpy(), val.numpy(), B.cpu().numpy())
