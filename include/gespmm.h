@@ -20,6 +20,10 @@
  *                                  (pytorch-custom/spmm_kernel.cu:381-423, 460-477)
  *   gespmm_read_mtx / _free        readMtx<float> + COO->CSR of the CLI
  *                                  (util/util.hpp:286-333, spmm_test.cu:557-581)
+ *   gespmm_csr_spmm_f32_host       the CLI's cudaMalloc / cudaMemcpy block around the launch
+ *                                  (spmm_test.cu:609-640)
+ *   gespmm_csr_spmm_f32_bparts,    no reference counterpart (the reference is single-GPU): B left
+ *   gespmm_ipc_*, _enable_peer_*   row-sharded across GPUs and gathered over NVLink by the kernel
  *
  * Conventions
  *   - All device pointers must live on the device that is current when the call is made.

@@ -271,6 +271,46 @@ def test_cuda_graph_capture(spmm, dev, oracle):
     assert np.array_equal(out.cpu().numpy(), oracle.spmm(rowptr, colind, None, B * 2))
 
 
+def test_concurrent_calls_from_host_threads_and_streams(spmm, dev, oracle):
+    """Re-entrancy: four host threads, each on its own stream, run different products at once (each thread gets its
+    own helper stream for the long-row kernel); every result matches the oracle."""
+    import threading
+    rng = np.random.default_rng(77)
+    jobs = []
+    for t in range(4):
+        M, N, K = 1500 + 100 * t, 1200, [64, 128, 256, 128][t]
+        deg = rng.integers(0, 20, M); deg[t] = 9000 + t  # one long row each
+        rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+        colind = rng.integers(0, N, rowptr[-1]).astype(np.int32)
+        B = rng.standard_normal((N, K)).astype(np.float32)
+        jobs.append((rowptr, colind, B))
+    results, errors = [None] * 4, []
+
+    def work(i):
+        try:
+            rowptr, colind, B = jobs[i]
+            st = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(st):
+                rp, ci, Bd = (torch.as_tensor(x, device=dev) for x in (rowptr, colind, B))
+                out = None
+                for _ in range(20):
+                    out = spmm.csr_spmm_no_edge_value(rp, ci, Bd)
+            st.synchronize()
+            results[i] = out.cpu().numpy()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for (rowptr, colind, B), got in zip(jobs, results):
+        want = oracle.spmm(rowptr, colind, None, B)
+        short = np.diff(rowptr) <= LONG
+        assert np.array_equal(got[short], want[short])
+        assert np.allclose(got[~short], want[~short], rtol=1e-4, atol=1e-3)
+
+
 def test_operator_rejects_bad_arguments(spmm, dev):
     rp = torch.zeros(5, dtype=torch.int32, device=dev); ci = torch.zeros(0, dtype=torch.int32, device=dev)
     B = torch.zeros(4, 8, device=dev)
