@@ -18,7 +18,7 @@ LONG_ROW = 4096
 
 # every symbol include/gespmm.h declares
 SYMBOLS = (
-    "gespmm_version", "gespmm_error_string", "gespmm_csr_spmm_f32", "gespmm_csr_spmm_f32_host", "gespmm_csr_spmm_f32_bparts", "gespmm_enable_peer_access", "gespmm_ipc_open", "gespmm_ipc_close", "gespmm_ipc_alloc", "gespmm_ipc_free",
+    "gespmm_version", "gespmm_error_string", "gespmm_csr_spmm_f32", "gespmm_csr_spmm_f32_host", "gespmm_csr_spmm_f32_bparts", "gespmm_csr_spmm_max_f32", "gespmm_enable_peer_access", "gespmm_ipc_open", "gespmm_ipc_close", "gespmm_ipc_alloc", "gespmm_ipc_free",
     "gespmm_csr2csc_workspace_bytes", "gespmm_csr2csc_f32", "gespmm_read_mtx", "gespmm_free_host",
 )
 
@@ -49,6 +49,8 @@ def lib():
         L.gespmm_csr_spmm_f32_bparts.restype = ctypes.c_int
         L.gespmm_csr_spmm_f32_bparts.argtypes = [i64, i64, i64, i64, p, p, p, ctypes.c_int, ctypes.POINTER(p),
                                                  ctypes.POINTER(i64), i64, p, i64, p]
+        L.gespmm_csr_spmm_max_f32.restype = ctypes.c_int
+        L.gespmm_csr_spmm_max_f32.argtypes = [i64, i64, i64, i64, p, p, p, p, i64, p, i64, ctypes.c_float, p]
         L.gespmm_enable_peer_access.restype = ctypes.c_int
         L.gespmm_enable_peer_access.argtypes = [ctypes.c_int]
         L.gespmm_ipc_open.restype = ctypes.c_int
@@ -88,6 +90,13 @@ def csr_spmm_f32(M, N, K, nnz, rowptr, colind, val, B, ldb, C, ldc, stream=None)
     rc = lib().gespmm_csr_spmm_f32(M, N, K, nnz, rowptr, colind, val or None, B, ldb, C, ldc, stream or None)
     if rc != OK:
         raise GespmmError(rc, "gespmm_csr_spmm_f32")
+
+
+def csr_spmm_max_f32(M, N, K, nnz, rowptr, colind, val, B, ldb, C, ldc, init=-10000.0, stream=None):
+    """Max-reduce variant (dgl-custom/binary_reduce_max.cu); init = -10000 is the reference's max_init()."""
+    rc = lib().gespmm_csr_spmm_max_f32(M, N, K, nnz, rowptr, colind, val or None, B, ldb, C, ldc, float(init), stream or None)
+    if rc != OK:
+        raise GespmmError(rc, "gespmm_csr_spmm_max_f32")
 
 
 def enable_peer_access(peer_device):

@@ -36,6 +36,11 @@
 //   in flight out of ~200 KB of rings), not by registers.  Unaligned operands / K % 4 != 0
 //   take the register variant (scalar loads, U rows in flight per warp).
 //
+// Reductions
+//   sum (the hot path) or max (gespmm_csr_spmm_max_f32: the reference's DGL patch,
+//   dgl-custom/binary_reduce_max.cu:18-168, `acc > x ? acc : x` from a caller-given start value).
+//   Max is order-independent, so long rows are bit-identical to a sequential walk as well.
+//
 // Long rows (kernel B, spmm_long_kernel: 8 warps per CTA)
 //   Rows with more than `long_row` nonzeros are skipped by kernel A.  Kernel B finds them
 //   without a list: every thread probes one 256-aligned nonzero position, binary-searches
@@ -91,6 +96,13 @@ template <> struct Pack<true> {
     static __device__ __forceinline__ void add(T &acc, const T &b) {
         acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
     }
+    static __device__ __forceinline__ T splat(float x) { return make_float4(x, x, x, x); }
+    // the reference's max_reduce: acc > x ? acc : x (dgl-custom/binary_reduce_max.cu:18-20), NaN behaviour included
+    static __device__ __forceinline__ void mx(T &acc, const T &b) {
+        acc.x = acc.x > b.x ? acc.x : b.x; acc.y = acc.y > b.y ? acc.y : b.y;
+        acc.z = acc.z > b.z ? acc.z : b.z; acc.w = acc.w > b.w ? acc.w : b.w;
+    }
+    static __device__ __forceinline__ T scaled(float a, const T &b) { return make_float4(a * b.x, a * b.y, a * b.z, a * b.w); }
 };
 template <> struct Pack<false> {
     using T = float;
@@ -100,6 +112,23 @@ template <> struct Pack<false> {
     static __device__ __forceinline__ void stcs(float *p, const T &a) { __stcs(p, a); }
     static __device__ __forceinline__ void fma(T &acc, float a, const T &b) { acc = fmaf(a, b, acc); }
     static __device__ __forceinline__ void add(T &acc, const T &b) { acc += b; }
+    static __device__ __forceinline__ T splat(float x) { return x; }
+    static __device__ __forceinline__ void mx(T &acc, const T &b) { acc = acc > b ? acc : b; }
+    static __device__ __forceinline__ T scaled(float a, const T &b) { return a * b; }
+};
+
+// The reduction over a row: sum (FFMA / FADD, start 0) or max (start `init`, the reference's -10000 or -inf).
+template <class P, bool VALUED, bool MAXR>
+struct Reduce {
+    using T = typename P::T;
+    static __device__ __forceinline__ T start(float init) { return MAXR ? P::splat(init) : P::zero(); }
+    static __device__ __forceinline__ void step(T &acc, float a, const T &b) {
+        if (MAXR) { if (VALUED) P::mx(acc, P::scaled(a, b)); else P::mx(acc, b); }
+        else { if (VALUED) P::fma(acc, a, b); else P::add(acc, b); }
+    }
+    static __device__ __forceinline__ void merge(T &acc, const T &other) {
+        if (MAXR) P::mx(acc, other); else P::add(acc, other);
+    }
 };
 
 __device__ __forceinline__ unsigned low_bits(int n) { return n >= 32 ? kFull : ((1u << n) - 1u); }
@@ -148,16 +177,20 @@ struct Operands {
     const float *B;
     float *C;
     int ldb, ldc;
+    float init;  // max-reduce: accumulator start and value of empty rows
     PeerMap peer;
 };
 
 // =================================================================================================
 // Register walker: U B-row packs in flight per lane, in registers.  Any alignment, any K.
 // =================================================================================================
-template <int V, bool VALUED, bool VEC4, int U>
+template <int V, bool VALUED, bool VEC4, int U, bool MAXR = false>
 struct Walker {
     using P = Pack<VEC4>;
     using T = typename P::T;
+    using R = Reduce<P, VALUED, MAXR>;
+    float init_v;
+    __device__ __forceinline__ T start() const { return R::start(init_v); }
     static constexpr int kStride = 32 * P::kWidth;  // floats between a lane's consecutive packs
     static constexpr int kRingBytes = 0;
 
@@ -171,6 +204,7 @@ struct Walker {
 
     __device__ __forceinline__ void init(const Operands &o, int col0, unsigned vm, int ln, unsigned /*ring*/) {
         colind = o.colind; val = o.val; Bl = o.B + col0; Cl = o.C + col0; ldb = o.ldb; ldc = o.ldc; vmask = vm; lane = ln;
+        init_v = o.init;
     }
 
     __device__ __forceinline__ void store_row(int row, const T (&acc)[V]) const {
@@ -200,15 +234,12 @@ struct Walker {
         for (int u = 0; u < U; u++) {
             if (FULL || (live & (1u << u))) {
 #pragma unroll
-                for (int v = 0; v < V; v++) {
-                    if (VALUED) P::fma(acc[v], a[u], b[u][v]);
-                    else P::add(acc[v], b[u][v]);
-                }
+                for (int v = 0; v < V; v++) R::step(acc[v], VALUED ? a[u] : 1.f, b[u][v]);
                 if (ends & (1u << u)) {  // last nonzero of the current row
                     store_row(rb + __ffs(rows_left) - 1, acc);
                     rows_left &= rows_left - 1;
 #pragma unroll
-                    for (int v = 0; v < V; v++) acc[v] = P::zero();
+                    for (int v = 0; v < V; v++) acc[v] = start();
                 }
             }
         }
@@ -271,8 +302,11 @@ __device__ __forceinline__ float4 lds128(unsigned saddr)
 // G rows per stage, NS stages (power of two, divides S32 = 32/G).  Stage j of a 32-nonzero chunk
 // lives in ring slot j % NS; the copies for stage j + NS - 1 are issued right before stage j is
 // consumed.  MASKED: some lanes' packs lie beyond K (K is not a multiple of 128*V).
-template <int V, bool VALUED, int G, int NS, int CP, bool MASKED, bool PEER = false>
+template <int V, bool VALUED, int G, int NS, int CP, bool MASKED, bool PEER = false, bool MAXR = false>
 struct WalkerRing {
+    using R = Reduce<Pack<true>, VALUED, MAXR>;
+    float init_v;
+    __device__ __forceinline__ float4 start() const { return R::start(init_v); }
     // what a lane keeps per prefetched nonzero: its column (B is one array) or the byte address of its
     // B row (B is a set of row blocks; the owner lookup is done once, by the lane that loaded the column)
     using Tok = typename std::conditional<PEER, unsigned long long, int>::type;
@@ -303,6 +337,7 @@ struct WalkerRing {
         ldb_bytes = (unsigned)o.ldb * 4u; ldc = o.ldc; vmask = vm; lane = ln;
         ring = ring_base + ln * 16;
         peer = &o.peer; lane_off = (unsigned)col0 * 4u;
+        init_v = o.init;
     }
 
     __device__ __forceinline__ Tok load_tok(int p) const {
@@ -362,7 +397,7 @@ struct WalkerRing {
         store_row(rb + __ffs(rows_left) - 1, acc);
         rows_left &= rows_left - 1;
 #pragma unroll
-        for (int v = 0; v < V; v++) acc[v] = P::zero();
+        for (int v = 0; v < V; v++) acc[v] = start();
     }
 
     template <bool FULL>
@@ -386,20 +421,14 @@ struct WalkerRing {
 #pragma unroll
                 for (int i = 0; i < UB; i++) {
 #pragma unroll
-                    for (int v = 0; v < V; v++) {
-                        if (VALUED) P::fma(acc[v], a[i], b[i][v]);
-                        else P::add(acc[v], b[i][v]);
-                    }
+                    for (int v = 0; v < V; v++) R::step(acc[v], VALUED ? a[i] : 1.f, b[i][v]);
                 }
             } else {
 #pragma unroll
                 for (int i = 0; i < UB; i++) {
                     if (FULL || pos0 + i0 + i < n) {
 #pragma unroll
-                        for (int v = 0; v < V; v++) {
-                            if (VALUED) P::fma(acc[v], a[i], b[i][v]);
-                            else P::add(acc[v], b[i][v]);
-                        }
+                        for (int v = 0; v < V; v++) R::step(acc[v], VALUED ? a[i] : 1.f, b[i][v]);
                         if (ends & (1u << i)) flush(acc, rows_left, rb);
                     }
                 }
@@ -493,7 +522,7 @@ spmm_flat_kernel(int M, int K, long long total_keys, int task, int long_row, con
             unsigned em = ~(nonempty | long_mask) & low_bits(nrows);
             T z[V];
 #pragma unroll
-            for (int v = 0; v < V; v++) z[v] = P::zero();
+            for (int v = 0; v < V; v++) z[v] = wk.start();
             while (em) {
                 wk.store_row(rb + __ffs(em) - 1, z);
                 em &= em - 1;
@@ -509,7 +538,7 @@ spmm_flat_kernel(int M, int K, long long total_keys, int task, int long_row, con
                 const int e = __shfl_sync(kFull, my_end, 31 - __clz(rows));
                 T acc[V];
 #pragma unroll
-                for (int v = 0; v < V; v++) acc[v] = P::zero();
+                for (int v = 0; v < V; v++) acc[v] = wk.start();
                 wk.stream(s, e, acc, my_end, rows, rb);
             }
             if (stop >= nrows) break;
@@ -586,7 +615,7 @@ spmm_long_kernel(int M, int K, int nnz, int long_row, const int *__restrict__ ro
         const int s = min(b, a + warp * seg), e = min(b, s + seg);
         T acc[V];
 #pragma unroll
-        for (int v = 0; v < V; v++) acc[v] = P::zero();
+        for (int v = 0; v < V; v++) acc[v] = wk.start();
         wk.stream(s, e, acc, 0, 0u, 0);
         T(*part)[V * 32] = s_part[i & 1];  // double-buffered: one barrier per row
 #pragma unroll
@@ -595,7 +624,7 @@ spmm_long_kernel(int M, int K, int nnz, int long_row, const int *__restrict__ ro
         for (int x = threadIdx.x; x < V * 32; x += kLongWarps * 32) {
             T sum = part[0][x];
 #pragma unroll
-            for (int w = 1; w < kLongWarps; w++) P::add(sum, part[w][x]);
+            for (int w = 1; w < kLongWarps; w++) WK::R::merge(sum, part[w][x]);
             const int c = blockIdx.y * (32 * V * W) + x * W;
             if (c < K) P::stcs(op.C + (long long)r * op.ldc + c, sum);
         }
@@ -616,7 +645,7 @@ spmm_long_kernel(int M, int K, int nnz, int long_row, const int *__restrict__ ro
             const int s = min(b, a + ((int)crank * kLongWarps + warp) * seg), e = min(b, s + seg);
             T acc[V];
 #pragma unroll
-            for (int v = 0; v < V; v++) acc[v] = P::zero();
+            for (int v = 0; v < V; v++) acc[v] = wk.start();
             wk.stream(s, e, acc, 0, 0u, 0);
 #pragma unroll
             for (int v = 0; v < V; v++) s_part[0][warp][v * 32 + lane] = acc[v];
@@ -624,14 +653,14 @@ spmm_long_kernel(int M, int K, int nnz, int long_row, const int *__restrict__ ro
             for (int x = threadIdx.x; x < V * 32; x += kLongWarps * 32) {
                 T sum = s_part[0][0][x];
 #pragma unroll
-                for (int w = 1; w < kLongWarps; w++) P::add(sum, s_part[0][w][x]);
+                for (int w = 1; w < kLongWarps; w++) WK::R::merge(sum, s_part[0][w][x]);
                 s_cpart[x] = sum;
             }
             cluster.sync();  // all CTA partials written
             if (crank == 0) {
                 for (int x = threadIdx.x; x < V * 32; x += kLongWarps * 32) {
                     T sum = s_cpart[x];
-                    for (unsigned c2 = 1; c2 < csize; c2++) P::add(sum, cluster.map_shared_rank(s_cpart, c2)[x]);
+                    for (unsigned c2 = 1; c2 < csize; c2++) WK::R::merge(sum, cluster.map_shared_rank(s_cpart, c2)[x]);
                     const int c = blockIdx.y * (32 * V * W) + x * W;
                     if (c < K) P::stcs(op.C + (long long)r * op.ldc + c, sum);
                 }
@@ -723,24 +752,8 @@ cudaError_t launch(const Args &a)
     return cudaGetLastError();
 }
 
-template <int V, bool VALUED, bool VEC4, int U, int MINB>
-cudaError_t launch_reg(const Args &a) { return launch<Walker<V, VALUED, VEC4, U>, V, VEC4, MINB>(a); }
-
-template <int V, bool VALUED, int G, int NS, int CP, int MINB>
-cudaError_t launch_ring(const Args &a, bool masked)
-{
-    return masked ? launch<WalkerRing<V, VALUED, G, NS, CP, true>, V, true, MINB>(a)
-                  : launch<WalkerRing<V, VALUED, G, NS, CP, false>, V, true, MINB>(a);
-}
-
-template <int V, bool VALUED>
-cudaError_t launch_peer(const Args &a, bool masked)
-{
-    constexpr int G = V == 1 ? 8 : (V == 2 ? 4 : 2);
-    constexpr int MINB = V == 1 ? 24 : (V == 2 ? 20 : (V == 3 ? 24 : 16));
-    return masked ? launch<WalkerRing<V, VALUED, G, 2, 0, true, true>, V, true, MINB>(a)
-                  : launch<WalkerRing<V, VALUED, G, 2, 0, false, true>, V, true, MINB>(a);
-}
+template <int V, bool VALUED, bool VEC4, int U, int MINB, bool MAXR = false>
+cudaError_t launch_reg(const Args &a) { return launch<Walker<V, VALUED, VEC4, U, MAXR>, V, VEC4, MINB>(a); }
 
 int env_int(const char *name, int dflt)
 {
@@ -748,46 +761,46 @@ int env_int(const char *name, int dflt)
     return (s && *s) ? atoi(s) : dflt;
 }
 
-// (V, variant) -> instantiation.  Variants other than 0 exist for tuning (GESPMM_VARIANT).
-template <bool VALUED, bool VEC4>
-cudaError_t launch_v(int V, int variant, bool masked, const Args &a)
+// Default ring shape per V: (G rows per stage, MINB CTAs per SM); two stages.
+template <int V> struct Shape;
+template <> struct Shape<1> { static constexpr int G = 8, MINB = 24; };
+template <> struct Shape<2> { static constexpr int G = 4, MINB = 20; };
+template <> struct Shape<3> { static constexpr int G = 2, MINB = 24; };
+template <> struct Shape<4> { static constexpr int G = 2, MINB = 16; };
+
+template <int V, bool VALUED, bool PEER, bool MAXR>
+cudaError_t launch_default(const Args &a, bool masked)
+{
+    constexpr int G = Shape<V>::G, MINB = Shape<V>::MINB;
+    return masked ? launch<WalkerRing<V, VALUED, G, 2, 0, true, PEER, MAXR>, V, true, MINB>(a)
+                  : launch<WalkerRing<V, VALUED, G, 2, 0, false, PEER, MAXR>, V, true, MINB>(a);
+}
+
+// variant 1 = register-staged walker on aligned operands (kept for comparisons, GESPMM_VARIANT=1)
+template <bool VALUED, bool VEC4, bool PEER, bool MAXR>
+cudaError_t dispatch(int V, int variant, bool masked, const Args &a)
 {
     if constexpr (!VEC4) {  // scalar instantiations: correctness path for odd K / unaligned operands
         switch (V) {
-            case 1: return launch_reg<1, VALUED, false, 8, 16>(a);
-            case 2: return launch_reg<2, VALUED, false, 4, 16>(a);
-            case 3: return launch_reg<3, VALUED, false, 4, 16>(a);
-            default: return launch_reg<4, VALUED, false, 4, 16>(a);
+            case 1: return launch_reg<1, VALUED, false, 8, 16, MAXR>(a);
+            case 2: return launch_reg<2, VALUED, false, 4, 16, MAXR>(a);
+            case 3: return launch_reg<3, VALUED, false, 4, 16, MAXR>(a);
+            default: return launch_reg<4, VALUED, false, 4, 16, MAXR>(a);
         }
     } else {
+        if (variant == 1 && !PEER && !MAXR) {
+            switch (V) {
+                case 1: return launch_reg<1, VALUED, true, 8, 24>(a);
+                case 2: return launch_reg<2, VALUED, true, 4, 24>(a);
+                case 3: return launch_reg<3, VALUED, true, 2, 16>(a);
+                default: return launch_reg<4, VALUED, true, 2, 16>(a);
+            }
+        }
         switch (V) {
-            case 1:
-                switch (variant) {
-                    case 1: return launch_reg<1, VALUED, true, 8, 24>(a);
-                    case 2: return launch_ring<1, VALUED, 4, 2, 0, 32>(a, masked);
-                    case 3: return launch_ring<1, VALUED, 8, 4, 0, 12>(a, masked);
-                    case 4: return launch_ring<1, VALUED, 16, 2, 0, 12>(a, masked);
-                    case 6: return launch_ring<1, VALUED, 8, 2, 1, 24>(a, masked);
-                    default: return launch_ring<1, VALUED, 8, 2, 0, 24>(a, masked);
-                }
-            case 2:
-                switch (variant) {
-                    case 1: return launch_reg<2, VALUED, true, 4, 24>(a);
-                    case 2: return launch_ring<2, VALUED, 2, 2, 0, 32>(a, masked);
-                    case 3: return launch_ring<2, VALUED, 8, 2, 0, 12>(a, masked);
-                    default: return launch_ring<2, VALUED, 4, 2, 0, 20>(a, masked);
-                }
-            case 3:
-                switch (variant) {
-                    case 1: return launch_reg<3, VALUED, true, 2, 16>(a);
-                    default: return launch_ring<3, VALUED, 2, 2, 0, 24>(a, masked);
-                }
-            default:
-                switch (variant) {
-                    case 1: return launch_reg<4, VALUED, true, 2, 16>(a);
-                    case 3: return launch_ring<4, VALUED, 4, 2, 0, 12>(a, masked);
-                    default: return launch_ring<4, VALUED, 2, 2, 0, 16>(a, masked);
-                }
+            case 1: return launch_default<1, VALUED, PEER, MAXR>(a, masked);
+            case 2: return launch_default<2, VALUED, PEER, MAXR>(a, masked);
+            case 3: return launch_default<3, VALUED, PEER, MAXR>(a, masked);
+            default: return launch_default<4, VALUED, PEER, MAXR>(a, masked);
         }
     }
 }
@@ -799,7 +812,7 @@ namespace {
 // Shared by the two entry points: argument checks, task window, dispatch.  `parts` == 0: B is one array.
 int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr, const int32_t *colind, const float *val,
              const float *B, int parts, const float *const *B_parts, const int64_t *part_begin, int64_t ldb, float *C,
-             int64_t ldc, void *stream)
+             int64_t ldc, void *stream, bool max_reduce = false, float init = 0.f)
 {
     if (M < 0 || N < 0 || K < 0 || nnz < 0) return GESPMM_ERR_INVALID_ARG;
     if (M > INT32_MAX - 64 || N > INT32_MAX || nnz > INT32_MAX - 64 || K > INT32_MAX || ldb >= (1LL << 30) || ldc > INT32_MAX)
@@ -859,18 +872,17 @@ int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr
     a.op.colind = colind; a.op.val = val; a.op.B = B; a.op.C = C; a.op.ldb = (int)ldb; a.op.ldc = (int)ldc;
     a.st = static_cast<cudaStream_t>(stream);
     a.overlap = env_int("GESPMM_OVERLAP", 1) != 0;
+    a.op.init = init;
     cudaError_t err;
-    if (parts > 0) {
-        switch (V) {
-            case 1: err = val ? launch_peer<1, true>(a, masked) : launch_peer<1, false>(a, masked); break;
-            case 2: err = val ? launch_peer<2, true>(a, masked) : launch_peer<2, false>(a, masked); break;
-            case 3: err = val ? launch_peer<3, true>(a, masked) : launch_peer<3, false>(a, masked); break;
-            default: err = val ? launch_peer<4, true>(a, masked) : launch_peer<4, false>(a, masked); break;
-        }
+    if (max_reduce) {
+        if (val) err = vec4 ? dispatch<true, true, false, true>(V, 0, masked, a) : dispatch<true, false, false, true>(V, 0, masked, a);
+        else err = vec4 ? dispatch<false, true, false, true>(V, 0, masked, a) : dispatch<false, false, false, true>(V, 0, masked, a);
+    } else if (parts > 0) {
+        err = val ? dispatch<true, true, true, false>(V, 0, masked, a) : dispatch<false, true, true, false>(V, 0, masked, a);
     } else if (val) {
-        err = vec4 ? launch_v<true, true>(V, variant, masked, a) : launch_v<true, false>(V, variant, masked, a);
+        err = vec4 ? dispatch<true, true, false, false>(V, variant, masked, a) : dispatch<true, false, false, false>(V, variant, masked, a);
     } else {
-        err = vec4 ? launch_v<false, true>(V, variant, masked, a) : launch_v<false, false>(V, variant, masked, a);
+        err = vec4 ? dispatch<false, true, false, false>(V, variant, masked, a) : dispatch<false, false, false, false>(V, variant, masked, a);
     }
     return err == cudaSuccess ? GESPMM_OK : GESPMM_ERR_CUDA;
 }
@@ -890,4 +902,11 @@ extern "C" int gespmm_csr_spmm_f32_bparts(int64_t M, int64_t N, int64_t K, int64
 {
     if (parts < 1) return GESPMM_ERR_INVALID_ARG;
     return run_spmm(M, N, K, nnz, rowptr, colind, val, nullptr, parts, B_parts, part_begin, ldb, C, ldc, stream);
+}
+
+extern "C" int gespmm_csr_spmm_max_f32(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr,
+                                       const int32_t *colind, const float *val, const float *B, int64_t ldb,
+                                       float *C, int64_t ldc, float init, void *stream)
+{
+    return run_spmm(M, N, K, nnz, rowptr, colind, val, B, 0, nullptr, nullptr, ldb, C, ldc, stream, true, init);
 }

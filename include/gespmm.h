@@ -16,6 +16,8 @@
  *                                  spmmWrapper (spmm_test.cu:456-492) and spmm_test0..4<T>
  *                                  (spmm_test.cu:64-454);  XTopoCsrmm<float>
  *                                  (dgl-custom/binary_reduce_sum.cu:309-335) has the same shape.
+ *   gespmm_csr_spmm_max_f32        topo*SPMMMaxKernel / XTopoCsrmmmax<float>
+ *                                  (dgl-custom/binary_reduce_max.cu:26-204)
  *   gespmm_csr2csc_f32             csr2cscKernel / csr2csc_cuda
  *                                  (pytorch-custom/spmm_kernel.cu:381-423, 460-477)
  *   gespmm_read_mtx / _free        readMtx<float> + COO->CSR of the CLI
@@ -94,6 +96,17 @@ int gespmm_csr_spmm_f32_bparts(int64_t M, int64_t N, int64_t K, int64_t nnz,
                                const int32_t *rowptr, const int32_t *colind, const float *val,
                                int parts, const float *const *B_parts, const int64_t *part_begin,
                                int64_t ldb, float *C, int64_t ldc, void *stream);
+
+/*
+ * C[r, :] = max over the nonzeros p of row r of (val[p] *) B[colind[p], :], starting from `init`, which is
+ * also what an empty row yields.  Replaces topoSimple/topoCache/topoCacheCoarsenSPMMMaxKernel and
+ * XTopoCsrmmmax<float> (dgl-custom/binary_reduce_max.cu:26-168, 170-204): pass val = NULL and
+ * init = -10000.0f for that code's exact results (its max_init(), :22-24), or -INFINITY for a true maximum.
+ * The comparison is the reference's `acc > x ? acc : x` (:18-20).
+ */
+int gespmm_csr_spmm_max_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
+                            const int32_t *rowptr, const int32_t *colind, const float *val,
+                            const float *B, int64_t ldb, float *C, int64_t ldc, float init, void *stream);
 
 /* Enable reads of `peer_device`'s memory from kernels on the current device (idempotent). */
 int gespmm_enable_peer_access(int peer_device);

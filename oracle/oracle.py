@@ -51,6 +51,7 @@ def lib():
         L = ctypes.CDLL(LIB)
         L.oracle_spmm_valued_f32.argtypes = [_i64, _i64, _p, _p, _p, _p, _i64, _p, _i64, ctypes.c_int, ctypes.c_int]
         L.oracle_spmm_unvalued_f32.argtypes = [_i64, _i64, _p, _p, _p, _i64, _p, _i64, ctypes.c_int]
+        L.oracle_spmm_max_f32.argtypes = [_i64, _i64, _p, _p, _p, _p, _i64, _p, _i64, ctypes.c_float, ctypes.c_int]
         L.oracle_spmm_f64.argtypes = [_i64, _i64, _p, _p, _p, _p, _i64, _p, _p, ctypes.c_int]
         L.oracle_ref_dispatch.argtypes = [_i64, _i64, _p, _p, _p]
         L.oracle_ref_dispatch.restype = ctypes.c_int
@@ -83,6 +84,17 @@ def spmm(rowptr, colind, val, B, fma=True, nthreads=0):
         val = _c(val, np.float32)
         lib().oracle_spmm_valued_f32(M, K, rowptr.ctypes.data, colind.ctypes.data, val.ctypes.data, B.ctypes.data, K,
                                      C.ctypes.data, K, 1 if fma else 0, nthreads)
+    return C
+
+
+def spmm_max(rowptr, colind, val, B, init=-10000.0, nthreads=0):
+    """Max-reduce restatement (dgl-custom/binary_reduce_max.cu); init = -10000 is the reference's max_init()."""
+    rowptr, colind, B = _c(rowptr, np.int32), _c(colind, np.int32), _c(B, np.float32)
+    M, K = rowptr.shape[0] - 1, B.shape[1]
+    C = np.empty((M, K), np.float32)
+    v = None if val is None else _c(val, np.float32)
+    lib().oracle_spmm_max_f32(M, K, rowptr.ctypes.data, colind.ctypes.data, None if v is None else v.ctypes.data,
+                              B.ctypes.data, K, C.ctypes.data, K, float(init), nthreads)
     return C
 
 

@@ -79,6 +79,31 @@ void oracle_spmm_unvalued_f32(int64_t M, int64_t K, const int32_t *rowptr, const
     }
 }
 
+/* ------------------------------------------------------------------------------------
+ * Max-reduce variant.  Follows max_reduce()/max_init() and the kernel loops of the DGL patch
+ * (dgl-custom/binary_reduce_max.cu:18-24, 26-168): acc = init; acc = acc > x ? acc : x over the row in
+ * CSR order; empty rows yield init (the reference's init is -10000).  val == NULL: x = B[col, k].
+ * ---------------------------------------------------------------------------------- */
+void oracle_spmm_max_f32(int64_t M, int64_t K, const int32_t *rowptr, const int32_t *colind, const float *val,
+                         const float *B, int64_t ldb, float *C, int64_t ldc, float init, int nthreads)
+{
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for schedule(dynamic, 256) if (nthreads != 1)
+#endif
+    for (int64_t i = 0; i < M; i++) {
+        float *crow = C + i * ldc;
+        for (int64_t k = 0; k < K; k++) crow[k] = init;
+        for (int32_t p = rowptr[i]; p < rowptr[i + 1]; p++) {
+            const float *brow = B + (int64_t)colind[p] * ldb;
+            for (int64_t k = 0; k < K; k++) {
+                const float x = val ? val[p] * brow[k] : brow[k];
+                crow[k] = crow[k] > x ? crow[k] : x;
+            }
+        }
+    }
+}
+
 /* fp64 golden of the same product (not in the reference; used to bound fp32 error). */
 void oracle_spmm_f64(int64_t M, int64_t K, const int32_t *rowptr, const int32_t *colind,
                      const float *val /* nullable */, const float *B, int64_t ldb, double *C,

@@ -130,6 +130,25 @@ def test_identities(oracle):
     assert z.shape == (M, 33) and not z.any()
 
 
+def test_max_reduce_restatement(oracle):
+    """dgl-custom/binary_reduce_max.cu semantics: start -10000, acc > x ? acc : x, empty rows keep the start value."""
+    rng = np.random.default_rng(3)
+    rowptr, colind = _rand_csr(rng, 50, 40, 300)
+    rowptr[10:] -= rowptr[10] - rowptr[9]  # make row 9 empty by shifting (keeps monotone)
+    rowptr = np.maximum.accumulate(rowptr).astype(np.int32)
+    colind = colind[: rowptr[-1]]
+    B = rng.standard_normal((40, 9)).astype(np.float32)
+    C = oracle.spmm_max(rowptr, colind, None, B)
+    for r in range(50):
+        cols = colind[rowptr[r]:rowptr[r + 1]]
+        want = np.maximum(B[cols].max(0), -10000.0) if len(cols) else np.full(9, -10000.0, np.float32)
+        assert np.array_equal(C[r], want.astype(np.float32))
+    assert np.array_equal(oracle.spmm_max(rowptr, colind, None, B - 20000.0), np.full((50, 9), -10000.0, np.float32))  # the sentinel's flaw
+    Cinf = oracle.spmm_max(rowptr, colind, None, B - 20000.0, init=-np.inf)
+    nonempty = np.diff(rowptr) > 0
+    assert np.isneginf(Cinf[~nonempty]).all() and (Cinf[nonempty] < -10000).all()
+
+
 def test_fp32_within_tolerance_of_fp64_golden(oracle):
     rng = np.random.default_rng(2)
     rowptr, colind = _rand_csr(rng, 500, 400, 60000)

@@ -243,6 +243,29 @@ def test_c_abi_b_given_as_row_blocks(dev, oracle, pkg, K):
         capi.csr_spmm_f32_bparts(M, N, K, nnz, rp.data_ptr(), ci.data_ptr(), None, [Bd.data_ptr()], [0, N - 1], K, C.data_ptr(), K)
 
 
+@pytest.mark.parametrize("K", [8, 33, 64, 128, 200, 512, 640])
+def test_max_reduce_matches_oracle_bitwise(dev, oracle, pkg, K):
+    """gespmm_csr_spmm_max_f32 (dgl-custom/binary_reduce_max.cu): max is order-independent, so every row --
+    short, long (> 4096) and huge (>= 32768, cluster path) -- is bit-identical to the sequential restatement."""
+    from gespmm_b200 import capi
+    rng = np.random.default_rng(41 + K)
+    M, N = 700, 3000
+    deg = rng.integers(0, 10, M); deg[[2, 300, 699]] = [40000, 5000, 4097]
+    rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    nnz = int(rowptr[-1])
+    colind = rng.integers(0, N, nnz).astype(np.int32)
+    val = rng.standard_normal(nnz).astype(np.float32)
+    B = (rng.standard_normal((N, K)) * 3).astype(np.float32)
+    rp, ci, v, Bd = (torch.as_tensor(x, device=dev) for x in (rowptr, colind, val, B))
+    for vv, init in ((None, -10000.0), (None, float("-inf")), (v, -10000.0)):
+        C = torch.full((M, K), float("nan"), device=dev)
+        capi.csr_spmm_max_f32(M, N, K, nnz, rp.data_ptr(), ci.data_ptr(), None if vv is None else vv.data_ptr(), Bd.data_ptr(), K,
+                              C.data_ptr(), K, init, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        want = oracle.spmm_max(rowptr, colind, None if vv is None else val, B, init=init)
+        assert np.array_equal(C.cpu().numpy(), want), (K, init)
+
+
 def test_c_abi_host_buffers(oracle, pkg):
     from gespmm_b200 import capi
     rng = np.random.default_rng(10)
