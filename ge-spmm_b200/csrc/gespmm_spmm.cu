@@ -53,6 +53,12 @@
 //   longest row of the matrix does not become the tail of the launch.  Kernel B runs on a
 //   helper stream, concurrently with kernel A.
 //
+// Sharded B (gespmm_csr_spmm_f32_bparts)
+//   B may be given as up to 8 row blocks in different allocations -- the other GPUs' blocks mapped
+//   through CUDA IPC.  The lane that loads a column resolves it to (block, local row) once and keeps
+//   the row's byte address instead of the column; the gather then runs on the peer address over
+//   NVLink.  Same walker, same order, same bits as with one contiguous B.
+//
 // Column mapping
 //   Lane l owns, for v < V, the float4 at column ((v*32 + l) * 4) of the current panel
 //   (panel = 128*V columns; blockIdx.y walks panels for K > 512).  One warp-wide copy

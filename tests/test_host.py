@@ -29,6 +29,16 @@ def test_library_exports_every_declared_symbol(pkg):
     assert capi.LONG_ROW == int(re.search(r"#define GESPMM_LONG_ROW (\d+)", header).group(1))
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/gespmm.h is the FFI contract: it must compile as C99 and as C++ with nothing but the standard headers."""
+    src = tmp_path / "t.c"
+    src.write_text('#include "gespmm.h"\nint main(void) { return gespmm_version() < 0; }\n')
+    for cc, std in (("gcc", "-std=c99"), ("g++", "-std=c++11")):
+        res = subprocess.run([cc, std, "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-x", "c" if cc == "gcc" else "c++",
+                              "-I", os.path.join(ROOT, "include"), str(src)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert res.returncode == 0, res.stdout
+
+
 def test_library_is_sm100a_only_and_free_of_forbidden_dependencies(pkg):
     from gespmm_b200 import build
     out = subprocess.run(["cuobjdump", "-lelf", build.LIB], stdout=subprocess.PIPE, text=True).stdout
