@@ -18,7 +18,7 @@ LONG_ROW = 4096
 
 # every symbol include/gespmm.h declares
 SYMBOLS = (
-    "gespmm_version", "gespmm_error_string", "gespmm_csr_spmm_f32", "gespmm_csr_spmm_f32_host", "gespmm_csr_spmm_f32_bparts", "gespmm_csr_spmm_max_f32", "gespmm_enable_peer_access", "gespmm_ipc_open", "gespmm_ipc_close", "gespmm_ipc_alloc", "gespmm_ipc_free",
+    "gespmm_version", "gespmm_error_string", "gespmm_csr_spmm_f32", "gespmm_csr_spmm_f32_host", "gespmm_csr_spmm_f32_bparts", "gespmm_csr_spmm_max_f32", "gespmm_row_sum_is_sequential", "gespmm_enable_peer_access", "gespmm_ipc_open", "gespmm_ipc_close", "gespmm_ipc_alloc", "gespmm_ipc_free",
     "gespmm_csr2csc_workspace_bytes", "gespmm_csr2csc_f32", "gespmm_read_mtx", "gespmm_free_host",
 )
 
@@ -51,6 +51,8 @@ def lib():
                                                  ctypes.POINTER(i64), i64, p, i64, p]
         L.gespmm_csr_spmm_max_f32.restype = ctypes.c_int
         L.gespmm_csr_spmm_max_f32.argtypes = [i64, i64, i64, i64, p, p, p, p, i64, p, i64, ctypes.c_float, p]
+        L.gespmm_row_sum_is_sequential.restype = ctypes.c_int
+        L.gespmm_row_sum_is_sequential.argtypes = [i64, i64]
         L.gespmm_enable_peer_access.restype = ctypes.c_int
         L.gespmm_enable_peer_access.argtypes = [ctypes.c_int]
         L.gespmm_ipc_open.restype = ctypes.c_int
@@ -97,6 +99,11 @@ def csr_spmm_max_f32(M, N, K, nnz, rowptr, colind, val, B, ldb, C, ldc, init=-10
     rc = lib().gespmm_csr_spmm_max_f32(M, N, K, nnz, rowptr, colind, val or None, B, ldb, C, ldc, float(init), stream or None)
     if rc != OK:
         raise GespmmError(rc, "gespmm_csr_spmm_max_f32")
+
+
+def row_sum_is_sequential(K, row_nnz):
+    """True if a row of ``row_nnz`` nonzeros at width K is summed in the reference's sequential order (bit-identical)."""
+    return bool(lib().gespmm_row_sum_is_sequential(int(K), int(row_nnz)))
 
 
 def enable_peer_access(peer_device):

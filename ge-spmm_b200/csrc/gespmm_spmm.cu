@@ -208,10 +208,18 @@ struct Walker {
     unsigned vmask;                 // bit v set: this lane's v-th pack is inside K
     int lane;
 
-    __device__ __forceinline__ void init(const Operands &o, int col0, unsigned vm, int ln, unsigned /*ring*/) {
-        colind = o.colind; val = o.val; Bl = o.B + col0; Cl = o.C + col0; ldb = o.ldb; ldc = o.ldc; vmask = vm; lane = ln;
+    // panel = blockIdx.y: this warp owns columns [panel * kPanel, (panel + 1) * kPanel) of B and C
+    static constexpr int kPanel = 32 * V * P::kWidth;
+    __device__ __forceinline__ void init(const Operands &o, int panel, int K, int ln, unsigned /*ring*/) {
+        const int col0 = panel * kPanel + ln * P::kWidth;
+        vmask = 0;
+#pragma unroll
+        for (int v = 0; v < V; v++)
+            if (col0 + v * kStride < K) vmask |= 1u << v;
+        colind = o.colind; val = o.val; Bl = o.B + col0; Cl = o.C + col0; ldb = o.ldb; ldc = o.ldc; lane = ln;
         init_v = o.init;
     }
+    __device__ __forceinline__ void finish(T (&)[V]) const {}  // a lane's accumulators are whole sums already
 
     __device__ __forceinline__ void store_row(int row, const T (&acc)[V]) const {
         float *c = Cl + (long long)row * ldc;
@@ -338,13 +346,20 @@ struct WalkerRing {
     const PeerMap *peer;        // PEER: the row blocks of B (in the kernel's parameter space)
     unsigned lane_off;          // PEER: byte offset of this lane's first owned column inside a B row
 
-    __device__ __forceinline__ void init(const Operands &o, int col0, unsigned vm, int ln, unsigned ring_base) {
+    static constexpr int kPanel = 128 * V;
+    __device__ __forceinline__ void init(const Operands &o, int panel, int K, int ln, unsigned ring_base) {
+        const int col0 = panel * kPanel + ln * 4;
+        vmask = 0;
+#pragma unroll
+        for (int v = 0; v < V; v++)
+            if (col0 + v * kStride < K) vmask |= 1u << v;
         colind = o.colind; val = o.val; Bl = reinterpret_cast<const char *>(o.B + col0); Cl = o.C + col0;
-        ldb_bytes = (unsigned)o.ldb * 4u; ldc = o.ldc; vmask = vm; lane = ln;
+        ldb_bytes = (unsigned)o.ldb * 4u; ldc = o.ldc; lane = ln;
         ring = ring_base + ln * 16;
         peer = &o.peer; lane_off = (unsigned)col0 * 4u;
         init_v = o.init;
     }
+    __device__ __forceinline__ void finish(T (&)[V]) const {}
 
     __device__ __forceinline__ Tok load_tok(int p) const {
         const int c = __ldcs(colind + p);
@@ -483,6 +498,185 @@ struct WalkerRing {
 };
 
 // =================================================================================================
+// Sub-warp ring walker for narrow B (K <= 64): NG nonzeros per warp-wide copy.
+// =================================================================================================
+// A B row of K <= 64 floats fills only LPR = 32 / NG lanes' float4 slices, so the ring walker above
+// spends a whole warp instruction (copy, read-back, shuffle, address) on 128-256 bytes.  Here the
+// warp is NG groups of LPR lanes and one step handles a QUAD of NG consecutive nonzeros of the flat
+// stream: group g copies / reads / accumulates nonzero (quad * NG + g), so every gather instruction
+// moves 512 bytes again.  Each group keeps its own partial sum of the current row (the nonzeros whose
+// stream position is g mod NG); at a row end the NG partials are added in a fixed butterfly order
+// (group g with g ^ NG/2, then ^ NG/4, ...) and group 0 stores the row.  Deterministic, but NOT the
+// reference's strictly sequential order: results differ from it by fp32 re-association (max-reduce:
+// still bit-identical).  gespmm_row_sum_is_sequential() tells callers which rows that applies to.
+template <int NG, bool VALUED, bool MAXR = false>
+struct WalkerSub {
+    using P = Pack<true>;
+    using T = float4;
+    using R = Reduce<P, VALUED, MAXR>;
+    static_assert(NG == 2 || NG == 4 || NG == 8, "2, 4 or 8 B rows per warp-wide copy");
+    static constexpr int LPR = 32 / NG;             // lanes per B row, one float4 each
+    static constexpr int Q = 32 / NG;               // quads per 32-nonzero chunk
+    static constexpr int QS = Q < 8 ? Q : 8;        // quads per ring stage
+    static constexpr int SN = QS * NG;              // nonzeros per stage
+    static constexpr int SPC = Q / QS;              // stages per chunk (1 or 2)
+    static constexpr int UB = 4;                    // quads read back from the ring per LDS batch
+    static constexpr int kStageBytes = QS * 512;
+    static constexpr int kRingBytes = 2 * kStageBytes;  // per warp: one stage in flight, one being consumed
+    static constexpr int kPanel = LPR * 4;          // columns one warp covers (>= K: a single panel)
+    static_assert(QS % UB == 0 && Q % QS == 0, "bad stage shape");
+
+    float init_v;
+    const int *__restrict__ colind;
+    const float *__restrict__ val;
+    const char *__restrict__ Bl;  // B + this lane's 4 columns (byte pointer)
+    float *__restrict__ Cl;
+    unsigned ldb_bytes;
+    int ldc;
+    int lane, g;                  // g = lane / LPR: which nonzero of a quad this lane works on
+    bool active;                  // this lane's 4 columns lie inside K
+    unsigned ring;                // shared-space address of this lane's 16 bytes in (stage 0, quad 0)
+
+    __device__ __forceinline__ T start() const { return R::start(init_v); }
+
+    __device__ __forceinline__ void init(const Operands &o, int /*panel*/, int K, int ln, unsigned ring_base) {
+        lane = ln; g = ln / LPR;
+        const int col0 = (ln % LPR) * 4;
+        active = col0 < K;
+        colind = o.colind; val = o.val; Bl = reinterpret_cast<const char *>(o.B + col0); Cl = o.C + col0;
+        ldb_bytes = (unsigned)o.ldb * 4u; ldc = o.ldc;
+        ring = ring_base + ln * 16;
+        init_v = o.init;
+    }
+
+    // whole-row values live in group 0 (after combine: in every group)
+    __device__ __forceinline__ void store_row(int row, const T (&acc)[1]) const {
+        if (g == 0 && active) P::stcs(Cl + (long long)row * ldc, acc[0]);
+    }
+
+    __device__ __forceinline__ void combine(T &t) const {
+#pragma unroll
+        for (int off = 16; off >= LPR; off >>= 1) {
+            T x;
+            x.x = __shfl_xor_sync(kFull, t.x, off); x.y = __shfl_xor_sync(kFull, t.y, off);
+            x.z = __shfl_xor_sync(kFull, t.z, off); x.w = __shfl_xor_sync(kFull, t.w, off);
+            R::merge(t, x);
+        }
+    }
+    // segment mode (kernel B): fold the groups' partials so that lanes [0, LPR) hold the segment's sums
+    __device__ __forceinline__ void finish(T (&acc)[1]) const { combine(acc[0]); }
+
+    __device__ __forceinline__ void flush(T &acc, unsigned &rows_left, int rb) const {
+        T t = acc;
+        combine(t);
+        if (g == 0 && active) P::stcs(Cl + (long long)(rb + __ffs(rows_left) - 1) * ldc, t);
+        rows_left &= rows_left - 1;
+        acc = start();
+    }
+
+    // copies for the SN nonzeros at chunk positions [pos0, pos0 + SN) of a chunk holding n nonzeros into
+    // the stage at byte offset `slot`; always exactly one commit group
+    template <bool FULL>
+    __device__ __forceinline__ void issue_impl(int cols, int pos0, int n, unsigned slot) const {
+#pragma unroll
+        for (int i0 = 0; i0 < QS; i0 += UB) {
+            const char *bp[UB];
+#pragma unroll
+            for (int i = 0; i < UB; i++) {
+                const int c = __shfl_sync(kFull, cols, pos0 + (i0 + i) * NG + g);
+                bp[i] = Bl + (unsigned long long)(unsigned)c * ldb_bytes;
+            }
+#pragma unroll
+            for (int i = 0; i < UB; i++)
+                if (active && (FULL || pos0 + (i0 + i) * NG + g < n)) cp_async16<0>(ring + slot + (i0 + i) * 512, bp[i]);
+        }
+        cp_async_commit();
+    }
+    __device__ __forceinline__ void issue(int cols, int pos0, int n, unsigned slot) const {
+        if (pos0 + SN <= n) issue_impl<true>(cols, pos0, n, slot);
+        else issue_impl<false>(cols, pos0, n, slot);
+    }
+
+    template <bool FULL>
+    __device__ __forceinline__ void consume_impl(float vals, int pos0, int n, unsigned endmask, T &acc,
+                                                 unsigned &rows_left, int rb, unsigned slot) const {
+#pragma unroll
+        for (int i0 = 0; i0 < QS; i0 += UB) {
+            T b[UB];
+            float a[UB];
+#pragma unroll
+            for (int i = 0; i < UB; i++) {
+                const int idx = pos0 + (i0 + i) * NG + g;
+                a[i] = 1.f;
+                if (VALUED) a[i] = __shfl_sync(kFull, vals, idx);
+                b[i] = P::zero();
+                if (active && (FULL || idx < n)) b[i] = lds128(ring + slot + (i0 + i) * 512);
+            }
+            const unsigned ends = (endmask >> (pos0 + i0 * NG)) & low_bits(UB * NG);
+            if (FULL && ends == 0u) {  // no row ends among these UB quads: straight accumulation
+#pragma unroll
+                for (int i = 0; i < UB; i++) R::step(acc, a[i], b[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < UB; i++) {
+                    const bool live = FULL || (pos0 + (i0 + i) * NG + g < n);
+                    unsigned e4 = (ends >> (i * NG)) & ((1u << NG) - 1u);  // bit x: a row ends at group x's nonzero
+                    int lo = 0;  // groups below `lo` already added their nonzero of this quad (to an earlier row)
+                    while (e4) {
+                        const int hi = __ffs(e4) - 1;
+                        if (live && g >= lo && g <= hi) R::step(acc, a[i], b[i]);
+                        flush(acc, rows_left, rb);
+                        lo = hi + 1;
+                        e4 &= e4 - 1;
+                    }
+                    if (live && g >= lo) R::step(acc, a[i], b[i]);
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void consume(float vals, int pos0, int n, unsigned endmask, T &acc, unsigned &rows_left,
+                                            int rb, unsigned slot) const {
+        if (pos0 + SN <= n) consume_impl<true>(vals, pos0, n, endmask, acc, rows_left, rb, slot);
+        else consume_impl<false>(vals, pos0, n, endmask, acc, rows_left, rb, slot);
+    }
+
+    // same contract as WalkerRing::stream; with rows == 0 the groups' partials are left in acc (see finish)
+    __device__ __forceinline__ void stream(int s, int e, T (&acc)[1], int my_end, unsigned rows, int rb) const {
+        int ccol = 0, ncol = 0, fcol = 0;
+        float cval = 1.f, nval = 1.f;
+        if (s + lane < e) {
+            ccol = __ldcs(colind + s + lane);
+            if (VALUED) cval = __ldcs(val + s + lane);
+        }
+        if (s + 32 + lane < e) ncol = __ldcs(colind + s + 32 + lane);
+        const bool my_row = (rows >> lane) & 1u;
+        unsigned rows_left = rows;
+        unsigned slot = 0;  // stage being consumed; the other one is being filled
+        issue(ccol, 0, min(32, e - s), 0);
+#pragma unroll 1
+        for (int p0 = s; p0 < e; p0 += 32) {
+            if (p0 + 64 + lane < e) fcol = __ldcs(colind + p0 + 64 + lane);
+            if (VALUED && p0 + 32 + lane < e) nval = __ldcs(val + p0 + 32 + lane);
+            const unsigned rel = (unsigned)(my_end - 1 - p0);
+            const unsigned endmask = __reduce_or_sync(kFull, (my_row && rel < 32u) ? (1u << rel) : 0u);
+            const int n = min(32, e - p0);
+            const int n_next = e - p0 - 32;
+#pragma unroll
+            for (int j = 0; j < SPC; j++) {
+                if (j * SN >= n) break;  // only in the last chunk, where nothing is in flight past it
+                const bool nxt = j + 1 >= SPC;  // the stage to fill next opens the next chunk
+                issue(nxt ? ncol : ccol, nxt ? 0 : (j + 1) * SN, nxt ? n_next : n, slot ^ kStageBytes);
+                cp_async_wait<1>();
+                consume(cval, j * SN, n, endmask, acc[0], rows_left, rb, slot);
+                slot ^= kStageBytes;
+            }
+            ccol = ncol; ncol = fcol; cval = nval;
+        }
+        cp_async_wait<0>();
+    }
+};
+
+// =================================================================================================
 // Kernel A: short rows.  One warp per CTA, one task per CTA.
 // =================================================================================================
 template <class WK, int V, bool VEC4, int MINB>
@@ -491,17 +685,11 @@ spmm_flat_kernel(int M, int K, long long total_keys, int task, int long_row, con
 {
     using P = Pack<VEC4>;
     using T = typename P::T;
-    constexpr int W = P::kWidth;
-    extern __shared__ __align__(16) unsigned char s_dyn[];  // gather ring (ring walker only)
+    extern __shared__ __align__(16) unsigned char s_dyn[];  // gather ring (ring walkers only)
 
     const int lane = threadIdx.x;
-    const int col0 = blockIdx.y * (32 * V * W) + lane * W;
-    unsigned vmask = 0;
-#pragma unroll
-    for (int v = 0; v < V; v++)
-        if (col0 + v * 32 * W < K) vmask |= 1u << v;
     WK wk;
-    wk.init(op, col0, vmask, lane, (unsigned)__cvta_generic_to_shared(s_dyn));
+    wk.init(op, blockIdx.y, K, lane, (unsigned)__cvta_generic_to_shared(s_dyn));
 
     // ---- this task's rows ---------------------------------------------------------------------
     const long long k0 = (long long)blockIdx.x * task;
@@ -603,13 +791,8 @@ spmm_long_kernel(int M, int K, int nnz, int long_row, const int *__restrict__ ro
     }
     __syncthreads();
 
-    const int col0 = blockIdx.y * (32 * V * W) + lane * W;
-    unsigned vmask = 0;
-#pragma unroll
-    for (int v = 0; v < V; v++)
-        if (col0 + v * 32 * W < K) vmask |= 1u << v;
     WK wk;
-    wk.init(op, col0, vmask, lane, (unsigned)__cvta_generic_to_shared(s_dyn) + warp * WK::kRingBytes);
+    wk.init(op, blockIdx.y, K, lane, (unsigned)__cvta_generic_to_shared(s_dyn) + warp * WK::kRingBytes);
 
     // ---- long rows: this CTA's 8 warps, contiguous segments, fixed-order combine ------------------
     const int nlist = min(s_n, kMaxList);
@@ -623,6 +806,7 @@ spmm_long_kernel(int M, int K, int nnz, int long_row, const int *__restrict__ ro
 #pragma unroll
         for (int v = 0; v < V; v++) acc[v] = wk.start();
         wk.stream(s, e, acc, 0, 0u, 0);
+        wk.finish(acc);
         T(*part)[V * 32] = s_part[i & 1];  // double-buffered: one barrier per row
 #pragma unroll
         for (int v = 0; v < V; v++) part[warp][v * 32 + lane] = acc[v];
@@ -631,7 +815,7 @@ spmm_long_kernel(int M, int K, int nnz, int long_row, const int *__restrict__ ro
             T sum = part[0][x];
 #pragma unroll
             for (int w = 1; w < kLongWarps; w++) WK::R::merge(sum, part[w][x]);
-            const int c = blockIdx.y * (32 * V * W) + x * W;
+            const int c = blockIdx.y * WK::kPanel + x * W;
             if (c < K) P::stcs(op.C + (long long)r * op.ldc + c, sum);
         }
     }
@@ -653,6 +837,7 @@ spmm_long_kernel(int M, int K, int nnz, int long_row, const int *__restrict__ ro
 #pragma unroll
             for (int v = 0; v < V; v++) acc[v] = wk.start();
             wk.stream(s, e, acc, 0, 0u, 0);
+            wk.finish(acc);
 #pragma unroll
             for (int v = 0; v < V; v++) s_part[0][warp][v * 32 + lane] = acc[v];
             __syncthreads();
@@ -667,7 +852,7 @@ spmm_long_kernel(int M, int K, int nnz, int long_row, const int *__restrict__ ro
                 for (int x = threadIdx.x; x < V * 32; x += kLongWarps * 32) {
                     T sum = s_cpart[x];
                     for (unsigned c2 = 1; c2 < csize; c2++) WK::R::merge(sum, cluster.map_shared_rank(s_cpart, c2)[x]);
-                    const int c = blockIdx.y * (32 * V * W) + x * W;
+                    const int c = blockIdx.y * WK::kPanel + x * W;
                     if (c < K) P::stcs(op.C + (long long)r * op.ldc + c, sum);
                 }
             }
@@ -720,8 +905,7 @@ Side *side_for_current_device()
 template <class WK, int V, bool VEC4, int MINB>
 cudaError_t launch(const Args &a)
 {
-    constexpr int W = VEC4 ? 4 : 1;
-    const unsigned panels = (unsigned)((a.K + 32 * V * W - 1) / (32 * V * W));
+    const unsigned panels = (unsigned)((a.K + WK::kPanel - 1) / WK::kPanel);
     const bool has_b = a.nnz > a.long_row;
     Side *sd = (has_b && a.overlap) ? side_for_current_device() : nullptr;
     if (has_b) {
@@ -780,6 +964,27 @@ cudaError_t launch_default(const Args &a, bool masked)
     constexpr int G = Shape<V>::G, MINB = Shape<V>::MINB;
     return masked ? launch<WalkerRing<V, VALUED, G, 2, 0, true, PEER, MAXR>, V, true, MINB>(a)
                   : launch<WalkerRing<V, VALUED, G, 2, 0, false, PEER, MAXR>, V, true, MINB>(a);
+}
+
+// Narrow B (K <= 64, aligned operands): NG = 2 / 4 / 8 nonzeros per warp-wide copy for K <= 64 / 32 / 16.
+template <bool VALUED, bool MAXR>
+cudaError_t dispatch_sub(int K, const Args &a)
+{
+    if (K > 32) return launch<WalkerSub<2, VALUED, MAXR>, 1, true, 24>(a);
+    if (K > 16) return launch<WalkerSub<4, VALUED, MAXR>, 1, true, 24>(a);
+    return launch<WalkerSub<8, VALUED, MAXR>, 1, true, 24>(a);
+}
+
+// Which walker sums the short rows of a product of width K on aligned operands.
+//   GESPMM_VARIANT unset / < 0 : automatic -- the sub-warp walker for K <= GESPMM_SUBWARP_MAX_K, else the ring walker
+//   0 : ring walker (the reference's sequential order for every K)   1 : register-staged walker (comparisons)
+//   2 : sub-warp walker wherever it applies (K <= 64)
+constexpr int kSubwarpMaxKDefault = 0;  // automatic choice off until measured on B200 (scripts/sweep.py --variants 0,2)
+bool use_subwarp(int64_t K, int variant)
+{
+    if (K > 64 || K % 4 != 0) return false;
+    if (variant == 2) return true;
+    return variant < 0 && K <= env_int("GESPMM_SUBWARP_MAX_K", kSubwarpMaxKDefault);
 }
 
 // variant 1 = register-staged walker on aligned operands (kept for comparisons, GESPMM_VARIANT=1)
@@ -862,7 +1067,8 @@ int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr
     // GESPMM_TASK / GESPMM_LONG / GESPMM_VARIANT / GESPMM_OVERLAP are tuning overrides (read per call).
     const int forced_task = env_int("GESPMM_TASK", 0);
     const int forced_long = env_int("GESPMM_LONG", 0);
-    const int variant = env_int("GESPMM_VARIANT", 0);
+    const int variant = env_int("GESPMM_VARIANT", -1);
+    const bool sub = vec4 && parts == 0 && use_subwarp(K, variant);
     const long long total = nnz + M;
     const long long warps_per_wave = 148LL * 24;
     const double keys_per_row = (double)total / (double)M;
@@ -880,7 +1086,10 @@ int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr
     a.overlap = env_int("GESPMM_OVERLAP", 1) != 0;
     a.op.init = init;
     cudaError_t err;
-    if (max_reduce) {
+    if (sub) {
+        if (max_reduce) err = val ? dispatch_sub<true, true>((int)K, a) : dispatch_sub<false, true>((int)K, a);
+        else err = val ? dispatch_sub<true, false>((int)K, a) : dispatch_sub<false, false>((int)K, a);
+    } else if (max_reduce) {
         if (val) err = vec4 ? dispatch<true, true, false, true>(V, 0, masked, a) : dispatch<true, false, false, true>(V, 0, masked, a);
         else err = vec4 ? dispatch<false, true, false, true>(V, 0, masked, a) : dispatch<false, false, false, true>(V, 0, masked, a);
     } else if (parts > 0) {
@@ -900,6 +1109,14 @@ extern "C" int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
                                    float *C, int64_t ldc, void *stream)
 {
     return run_spmm(M, N, K, nnz, rowptr, colind, val, B, 0, nullptr, nullptr, ldb, C, ldc, stream);
+}
+
+extern "C" int gespmm_row_sum_is_sequential(int64_t K, int64_t row_nnz)
+{
+    const int forced_long = env_int("GESPMM_LONG", 0);
+    if (row_nnz > (forced_long >= kMinLong ? forced_long : GESPMM_LONG_ROW)) return 0;  // segmented (kernel B)
+    if (row_nnz > 1 && use_subwarp(K, env_int("GESPMM_VARIANT", -1))) return 0;       // per-group partial sums
+    return 1;
 }
 
 extern "C" int gespmm_csr_spmm_f32_bparts(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr,

@@ -127,6 +127,18 @@ int gespmm_ipc_free(void *dptr);
 #define GESPMM_LONG_ROW 4096
 
 /*
+ * 1 if gespmm_csr_spmm_f32 sums a row of `row_nnz` nonzeros of a product of width K in the reference's
+ * strictly sequential CSR order (its result is then bit-identical to the reference kernels'), 0 if the
+ * row's sum is re-associated (deterministically): rows longer than GESPMM_LONG_ROW, and -- where the
+ * sub-warp walker for narrow B (K <= 64: several nonzeros per warp-wide gather, one partial sum per
+ * lane group) is in use -- rows of more than one nonzero.  Assumes the aligned fast path (K, ldb, ldc
+ * multiples of 4, 16-byte aligned B and C); other operands always take the sequential walker for rows up
+ * to GESPMM_LONG_ROW.  Pure function of its arguments and of the GESPMM_* tuning environment variables.
+ * (New: every reference kernel is sequential, pytorch-custom/spmm_kernel.cu:56-59, 165-168.)
+ */
+int gespmm_row_sum_is_sequential(int64_t K, int64_t row_nnz);
+
+/*
  * Same product with HOST buffers: allocates device buffers on `device`, copies in, runs
  * gespmm_csr_spmm_f32, copies C back, frees, synchronises.  For callers without their own
  * device memory management (what the CLI does by hand, spmm_test.cu:609-640).

@@ -88,6 +88,28 @@ def test_argument_validation_without_a_device(pkg):
             capi.csr_spmm_host(rp, np.zeros(0, np.int32), None, B)
 
 
+def test_row_sum_order_query(pkg, monkeypatch):
+    """gespmm_row_sum_is_sequential is a pure function of (K, row length) and the tuning environment."""
+    from gespmm_b200 import capi
+    for name in ("GESPMM_VARIANT", "GESPMM_SUBWARP_MAX_K", "GESPMM_LONG"):
+        monkeypatch.delenv(name, raising=False)
+    for K in (1, 4, 32, 64, 100, 128, 512, 4096):
+        assert capi.row_sum_is_sequential(K, 0) and capi.row_sum_is_sequential(K, 1)
+        assert not capi.row_sum_is_sequential(K, capi.LONG_ROW + 1)
+        assert capi.row_sum_is_sequential(K, capi.LONG_ROW) == capi.row_sum_is_sequential(K, 2)
+    assert capi.row_sum_is_sequential(128, capi.LONG_ROW) and capi.row_sum_is_sequential(68, 2) and capi.row_sum_is_sequential(30, 2)
+    monkeypatch.setenv("GESPMM_VARIANT", "0")  # the ring walker: sequential for every K
+    assert all(capi.row_sum_is_sequential(K, capi.LONG_ROW) for K in (4, 16, 32, 64))
+    monkeypatch.setenv("GESPMM_VARIANT", "2")  # the sub-warp walker wherever it applies: K <= 64, K % 4 == 0
+    assert not any(capi.row_sum_is_sequential(K, 2) for K in (4, 16, 32, 48, 64))
+    assert all(capi.row_sum_is_sequential(K, 2) for K in (3, 30, 65, 68, 128))
+    monkeypatch.delenv("GESPMM_VARIANT")
+    monkeypatch.setenv("GESPMM_SUBWARP_MAX_K", "32")
+    assert not capi.row_sum_is_sequential(32, 2) and capi.row_sum_is_sequential(64, 2)
+    monkeypatch.setenv("GESPMM_LONG", "1024")
+    assert not capi.row_sum_is_sequential(128, 1025) and capi.row_sum_is_sequential(128, 1024)
+
+
 # ---- .mtx reader -----------------------------------------------------------------------------------
 
 def _csr_to_coo(rowptr, colind):

@@ -3,9 +3,9 @@ oracle, against the reference's own kernels compiled from /root/reference (oracl
 it travelled), and -- at BASELINE.json's full sizes -- through size-independent properties.
 
 Bar (BASELINE.json north_star): within 1e-4 relative fp32 of the reference.  What is actually
-asserted is stronger: BIT-EXACT for every row of at most GESPMM_LONG_ROW nonzeros (the kernel
-keeps the reference's per-element summation order), and |diff| <= 1e-4 * max(|ref|, sum|a||b|)
-for the segmented long rows.
+asserted is stronger: BIT-EXACT for every row the library sums in the reference's sequential order
+(gespmm_row_sum_is_sequential: rows of at most GESPMM_LONG_ROW nonzeros, unless the sub-warp walker
+for K <= 64 is in use), and |diff| <= 1e-4 * max(|ref|, sum|a||b|) for the re-associated rows.
 """
 import os
 import subprocess
@@ -60,18 +60,30 @@ def _run(spmm, dev, rowptr, colind, val, B):
     return out
 
 
+def _sequential_rows(rowptr, K):
+    """Rows the library sums in the reference's order (include/gespmm.h: gespmm_row_sum_is_sequential)."""
+    from gespmm_b200 import capi
+    deg = np.diff(rowptr)
+    assert capi.row_sum_is_sequential(K, 1) and capi.row_sum_is_sequential(K, 0)
+    assert not capi.row_sum_is_sequential(K, LONG + 1)
+    if capi.row_sum_is_sequential(K, 2):
+        assert capi.row_sum_is_sequential(K, LONG)
+        return deg <= LONG
+    return deg <= 1
+
+
 def _check(oracle, rowptr, colind, val, B, C):
-    """bit-exact on short rows, 1e-4 of sum|a||b| on long rows; returns number of long rows."""
+    """bit-exact on sequentially summed rows, 1e-4 of sum|a||b| on the others; returns number of long rows."""
     C = C.cpu().numpy()
     want = oracle.spmm(rowptr, colind, val, B, fma=True)
-    long_rows = np.diff(rowptr) > LONG
+    seq = _sequential_rows(rowptr, B.shape[1])
     assert C.shape == want.shape
-    assert np.array_equal(C[~long_rows], want[~long_rows]), "short rows must be bit-identical to the oracle"
-    if long_rows.any():
+    assert np.array_equal(C[seq], want[seq]), "sequentially summed rows must be bit-identical to the oracle"
+    if not seq.all():
         G, mag = oracle.spmm_f64(rowptr, colind, val, B)
         err = np.abs(C.astype(np.float64) - G)
         assert (err <= RTOL * np.maximum(np.abs(G), mag) + 1e-30).all()
-    return int(long_rows.sum())
+    return int((np.diff(rowptr) > LONG).sum())
 
 
 def _rand_csr(rng, M, N, nnz, empty_frac=0.0):
@@ -104,7 +116,8 @@ def test_bundled_graphs_match_oracle_and_reference_kernels(spmm, dev, oracle, go
             rp, ci, Bd = (torch.as_tensor(x, device=dev) for x in (rowptr, colind, B))
             R = ref.csr_spmm_no_edge_value(rp, ci, Bd) if v is None else ref.csr_spmm(rp, ci, torch.as_tensor(v, device=dev), Bd)
             torch.cuda.synchronize()
-            assert torch.equal(C, R), "must be bit-identical to pytorch-custom/spmm_kernel.cu on the same inputs"
+            seq = torch.from_numpy(_sequential_rows(rowptr, K)).to(dev)
+            assert torch.equal(C[seq], R[seq]), "must be bit-identical to pytorch-custom/spmm_kernel.cu on the same inputs"
 
 
 def test_reference_cli_kernels_agree_bitwise(spmm, dev, oracle, golden_csr, ref_cli):
@@ -175,6 +188,52 @@ def test_long_rows_segmented_path(spmm, dev, oracle, K):
         assert torch.equal(C1, C2), "segmented path must be deterministic"
 
 
+@pytest.mark.parametrize("K", [4, 8, 12, 16, 20, 24, 32, 36, 48, 60, 64])
+def test_subwarp_walker_for_narrow_B(spmm, dev, oracle, pkg, monkeypatch, K):
+    """GESPMM_VARIANT=2: 2 / 4 / 8 nonzeros per warp-wide gather for K <= 64 / 32 / 16.  Integer-valued operands make
+    every fp32 sum exact, so the result must equal the oracle bit for bit whatever the association; real-valued
+    operands must stay within 1e-4 of the fp64 golden, be deterministic, and rows of <= 1 nonzero stay bit-exact.
+    Empty rows, rows ending at every position of a quad, long (> 4096) and huge (>= 32768) rows, max-reduce."""
+    from gespmm_b200 import capi
+    monkeypatch.setenv("GESPMM_VARIANT", "2")
+    assert not capi.row_sum_is_sequential(K, 2) and capi.row_sum_is_sequential(K, 1)
+    assert capi.row_sum_is_sequential(128, LONG)  # wider products are not affected
+    rng = np.random.default_rng(500 + K)
+    M, N = 2500, 3000
+    deg = rng.integers(0, 9, M)
+    deg[rng.random(M) < 0.3] = 0
+    deg[[5, 6, 900, 2499]] = [40000, 4097, 700, 33000]
+    deg[1000:1100] = rng.integers(20, 200, 100)
+    rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    nnz = int(rowptr[-1])
+    colind = rng.integers(0, N, nnz).astype(np.int32)
+    Bi = rng.integers(-8, 9, (N, K)).astype(np.float32)
+    vi = rng.integers(-2, 3, nnz).astype(np.float32)
+    for v in (None, vi):
+        C = _run(spmm, dev, rowptr, colind, v, Bi).cpu().numpy()
+        assert np.array_equal(C, oracle.spmm(rowptr, colind, v, Bi, fma=True)), "exact (integer) sums must not depend on the order"
+    Bf = rng.standard_normal((N, K)).astype(np.float32)
+    vf = rng.standard_normal(nnz).astype(np.float32)
+    for v in (None, vf):
+        C1 = _run(spmm, dev, rowptr, colind, v, Bf)
+        assert _check(oracle, rowptr, colind, v, Bf, C1) == 3
+        assert torch.equal(C1, _run(spmm, dev, rowptr, colind, v, Bf)), "must be deterministic"
+    rp, ci, v, Bd = (torch.as_tensor(x, device=dev) for x in (rowptr, colind, vf, Bf))
+    for vv in (None, v):
+        C = torch.full((M, K), float("nan"), device=dev)
+        capi.csr_spmm_max_f32(M, N, K, nnz, rp.data_ptr(), ci.data_ptr(), None if vv is None else vv.data_ptr(), Bd.data_ptr(), K,
+                              C.data_ptr(), K, -10000.0, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(C.cpu().numpy(), oracle.spmm_max(rowptr, colind, None if vv is None else vf, Bf, init=-10000.0))
+    # not a multiple of 4 / unaligned: the request is ignored, the sequential scalar walker runs
+    monkeypatch.setenv("GESPMM_VARIANT", "2")
+    B3 = rng.standard_normal((N, K - 1)).astype(np.float32)
+    C = _run(spmm, dev, rowptr, colind, None, B3).cpu().numpy()
+    want = oracle.spmm(rowptr, colind, None, B3)
+    short = np.diff(rowptr) <= LONG
+    assert np.array_equal(C[short], want[short])
+
+
 def test_skewed_rmat_graph(spmm, dev, oracle, pkg):
     from gespmm_b200 import graphs
     rowptr, colind = graphs.rmat(N=200_000, nnz=4_000_000, seed=4)
@@ -237,8 +296,16 @@ def test_c_abi_b_given_as_row_blocks(dev, oracle, pkg, K):
             capi.csr_spmm_f32(M, N, K, nnz, rp.data_ptr(), ci.data_ptr(), None if vv is None else vv.data_ptr(), Bd.data_ptr(), K,
                               whole.data_ptr(), K, torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
-            assert torch.equal(C, whole), (K, bounds)
-            _check(oracle, rowptr, colind, None if vv is None else val, B, C)
+            if capi.row_sum_is_sequential(K, 2):  # same walker either way: long rows are segmented identically too
+                assert torch.equal(C, whole), (K, bounds)
+            else:
+                seq = torch.from_numpy(_sequential_rows(rowptr, K)).to(dev)
+                assert torch.equal(C[seq], whole[seq]), (K, bounds)
+            _check(oracle, rowptr, colind, None if vv is None else val, B, whole)
+            # the sharded-B walker is always the sequential ring walker
+            want = oracle.spmm(rowptr, colind, None if vv is None else val, B, fma=True)
+            short = np.diff(rowptr) <= LONG
+            assert np.array_equal(C.cpu().numpy()[short], want[short])
     with pytest.raises(capi.GespmmError):  # blocks must cover [0, N)
         capi.csr_spmm_f32_bparts(M, N, K, nnz, rp.data_ptr(), ci.data_ptr(), None, [Bd.data_ptr()], [0, N - 1], K, C.data_ptr(), K)
 
@@ -329,7 +396,7 @@ def test_concurrent_calls_from_host_threads_and_streams(spmm, dev, oracle):
     assert not errors, errors
     for (rowptr, colind, B), got in zip(jobs, results):
         want = oracle.spmm(rowptr, colind, None, B)
-        short = np.diff(rowptr) <= LONG
+        short = _sequential_rows(rowptr, B.shape[1])
         assert np.array_equal(got[short], want[short])
         assert np.allclose(got[~short], want[~short], rtol=1e-4, atol=1e-3)
 
