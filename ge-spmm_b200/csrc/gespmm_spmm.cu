@@ -606,29 +606,31 @@ struct WalkerSub {
             float a[UB];
 #pragma unroll
             for (int i = 0; i < UB; i++) {
-                const int idx = pos0 + (i0 + i) * NG + g;
-                a[i] = 1.f;
-                if (VALUED) a[i] = __shfl_sync(kFull, vals, idx);
-                b[i] = P::zero();
-                if (active && (FULL || idx < n)) b[i] = lds128(ring + slot + (i0 + i) * 512);
+                // read back unconditionally: a slice that was not copied this time (nonzero beyond n, columns
+                // beyond K) holds stale ring bytes that are never added to anything that is stored
+                a[i] = VALUED ? __shfl_sync(kFull, vals, pos0 + (i0 + i) * NG + g) : 1.f;
+                b[i] = lds128(ring + slot + (i0 + i) * 512);
             }
-            const unsigned ends = (endmask >> (pos0 + i0 * NG)) & low_bits(UB * NG);
-            if (FULL && ends == 0u) {  // no row ends among these UB quads: straight accumulation
+            if (FULL && ((endmask >> (pos0 + i0 * NG)) & low_bits(UB * NG)) == 0u) {  // no row ends in these UB quads
 #pragma unroll
                 for (int i = 0; i < UB; i++) R::step(acc, a[i], b[i]);
-            } else {
+                continue;
+            }
 #pragma unroll
-                for (int i = 0; i < UB; i++) {
-                    const bool live = FULL || (pos0 + (i0 + i) * NG + g < n);
-                    unsigned e4 = (ends >> (i * NG)) & ((1u << NG) - 1u);  // bit x: a row ends at group x's nonzero
+            for (int i = 0; i < UB; i++) {
+                const bool live = FULL || (pos0 + (i0 + i) * NG + g < n);
+                unsigned e4 = (endmask >> (pos0 + (i0 + i) * NG)) & ((1u << NG) - 1u);  // bit x: a row ends at group x's nonzero
+                if (e4 == 0u) {  // warp-uniform: no row ends inside this quad (the common case for rows >> NG)
+                    if (live) R::step(acc, a[i], b[i]);
+                } else {
                     int lo = 0;  // groups below `lo` already added their nonzero of this quad (to an earlier row)
-                    while (e4) {
+                    do {
                         const int hi = __ffs(e4) - 1;
                         if (live && g >= lo && g <= hi) R::step(acc, a[i], b[i]);
                         flush(acc, rows_left, rb);
                         lo = hi + 1;
                         e4 &= e4 - 1;
-                    }
+                    } while (e4);
                     if (live && g >= lo) R::step(acc, a[i], b[i]);
                 }
             }
@@ -979,7 +981,7 @@ cudaError_t dispatch_sub(int K, const Args &a)
 //   GESPMM_VARIANT unset / < 0 : automatic -- the sub-warp walker for K <= GESPMM_SUBWARP_MAX_K, else the ring walker
 //   0 : ring walker (the reference's sequential order for every K)   1 : register-staged walker (comparisons)
 //   2 : sub-warp walker wherever it applies (K <= 64)
-constexpr int kSubwarpMaxKDefault = 0;  // automatic choice off until measured on B200 (scripts/sweep.py --variants 0,2)
+constexpr int kSubwarpMaxKDefault = 64;  // measured on B200 (profiles/r01_sweep_narrow.txt): 1.1-6x the ring walker at K <= 64
 bool use_subwarp(int64_t K, int variant)
 {
     if (K > 64 || K % 4 != 0) return false;
@@ -1073,6 +1075,9 @@ int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr
     const long long warps_per_wave = 148LL * 24;
     const double keys_per_row = (double)total / (double)M;
     long long tk = ((long long)(48.0 * sqrt(keys_per_row)) + 31) & ~31LL;
+    // the sub-warp walker spends 1/NG of the instructions per nonzero, so a task's start-up weighs NG times more:
+    // measured optima are 512 (cit-Patents shape) to 1024 (ogbn-products, R-MAT, Reddit shapes) at K = 16, 32
+    if (sub) tk *= (K > 32 ? 2 : (K > 16 ? 4 : 8));
     const long long cap = (total / (8 * warps_per_wave)) & ~31LL;
     if (tk > cap) tk = cap;
     int task = (int)(tk < 32 ? 32 : (tk > kMaxTask ? kMaxTask : tk));

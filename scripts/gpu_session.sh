@@ -1,0 +1,62 @@
+#!/bin/bash
+# One bounded GPU session (run through gpurun from the repo root): every step under its own timeout, most
+# important first, everything into gpurun_out/.  Usage: bash scripts/gpu_session.sh [steps...]
+#   steps: subwarp sweep ksweep suite seq auto64 bench smoke sanitize ncu   (default: all, in that order)
+cd "$(dirname "$0")/.." || exit 1
+O=gpurun_out
+mkdir -p $O
+STEPS=${*:-subwarp sweep suite auto64 bench smoke sanitize ncu}
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > $O/gpu.txt 2>&1
+note() { echo "$(date +%T) $*" | tee -a $O/status.txt; }
+note "session start: $STEPS"
+for step in $STEPS; do
+  case $step in
+    subwarp)  # first contact with the sub-warp walker (GESPMM_VARIANT=2 inside the test)
+      timeout 300 python -m pytest tests/test_spmm_gpu.py -q -m gpu -k "subwarp" > $O/t_subwarp.log 2>&1; note "subwarp rc=$?" ;;
+    sweep)    # ring vs sub-warp walker, K <= 64, four graph shapes
+      timeout 420 python scripts/sweep_narrow.py > $O/sweep_narrow.txt 2> $O/sweep_narrow.err; note "sweep rc=$?" ;;
+    ksweep)   # the shipped configuration next to the reference kernel, every BASELINE shape
+      timeout 600 python scripts/sweep_narrow.py --workloads products --Ks 32,64,128,256,512 --variants -1 --tasks 0 --valued 1 --ref > $O/ksweep.txt 2> $O/ksweep.err
+      timeout 600 python scripts/sweep_narrow.py --workloads reddit,citpatents,rmat --rmat-scale 1.0 --Ks 128,256 --variants -1 --tasks 0 --valued 1 --ref >> $O/ksweep.txt 2>> $O/ksweep.err
+      note "ksweep rc=$?" ;;
+    suite)    # the whole GPU suite with default settings
+      timeout 900 python -m pytest tests -q -m gpu > $O/t_default.log 2>&1; note "suite rc=$?" ;;
+    seq)      # the SpMM suite with the sequential ring walker forced for every K
+      GESPMM_VARIANT=0 timeout 600 python -m pytest tests/test_spmm_gpu.py -q -m gpu > $O/t_seq.log 2>&1; note "seq rc=$?" ;;
+    auto64)   # the SpMM suite with the sub-warp walker chosen automatically for K <= 64
+      GESPMM_SUBWARP_MAX_K=64 timeout 600 python -m pytest tests/test_spmm_gpu.py -q -m gpu > $O/t_auto64.log 2>&1; note "auto64 rc=$?" ;;
+    bench)
+      timeout 600 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; note "bench rc=$?"
+      timeout 300 python bench.py --impl reference > $O/bench_n1_reference.json 2> $O/bench_n1_reference.err; note "bench reference rc=$?" ;;
+    smoke)
+      timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; note "smoke rc=$?" ;;
+    sanitize) # compute-sanitizer over the sub-warp kernels through the CLI
+      python - > $O/sanitize_gen.log 2>&1 <<'PY'
+import sys, numpy as np
+sys.path.insert(0, '.')
+import __graft_entry__ as e
+e.load_package()
+from gespmm_b200 import graphs
+rng = np.random.default_rng(0)
+M = 3000
+deg = rng.integers(0, 9, M); deg[rng.random(M) < 0.3] = 0
+deg[[5, 700, 701, 2999]] = [40000, 5000, 4097, 9000]
+rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+colind = rng.integers(0, M, rowptr[-1]).astype(np.int32)
+graphs.write_mtx('gpurun_out/sanitize.mtx', rowptr, colind)
+PY
+      for tool in memcheck racecheck; do
+        echo "== $tool (GESPMM_VARIANT=2, K=16,32,64)" >> $O/sanitize_subwarp.txt
+        GESPMM_VARIANT=2 timeout 300 compute-sanitizer --tool $tool --error-exitcode 9 ge-spmm_b200/bin/spmm_test $O/sanitize.mtx 0 \
+            --K 16,32,64 --iters 2 --validate --out $O/sanitize.csv 2>&1 | grep -E "SUMMARY|validate|WA|Error|error" | head -12 >> $O/sanitize_subwarp.txt
+      done
+      note "sanitize done" ;;
+    ncu)      # one full capture of each walker's kernel A on the ogbn-products shape, K = 32
+      for v in 2 0; do
+        GESPMM_VARIANT=$v timeout 400 ncu --set full --clock-control none --import-source on -k regex:spmm_flat_kernel --launch-skip 3 -c 1 \
+            -f -o $O/ncu_products_K32_v$v python scripts/sweep.py --workload products --K 32 --variants $v --iters 1 > $O/ncu_v$v.log 2>&1
+        note "ncu v$v rc=$?"
+      done ;;
+  esac
+done
+note "session end"

@@ -1,8 +1,10 @@
 #!/usr/bin/env python
-"""Narrow-B sweep (GPU): ring walker (GESPMM_VARIANT=0, sequential order) against the sub-warp walker
-(GESPMM_VARIANT=2) for K <= 64 over several graph shapes and task windows, one process, one JSON line per run.
+"""Multi-shape sweep (GPU), one process, one JSON line per run.  Default: the ring walker (GESPMM_VARIANT=0,
+sequential order) against the sub-warp walker (GESPMM_VARIANT=2) for K <= 64 over four graph shapes and task windows:
     python scripts/sweep_narrow.py [--workloads products,reddit,citpatents,rmat] [--Ks 16,32,64] [--tasks 0,256,512,1024]
-Every variant's result is compared with the ring walker's: max |diff| relative to max |C| (re-association only).
+K sweep of the shipped configuration next to the reference kernel (spmm_test2<float>, tile_row 8) on the same GPU:
+    python scripts/sweep_narrow.py --workloads products --Ks 32,64,128,256,512 --variants -1 --tasks 0 --valued 1 --ref
+Every run's result is compared with the first run's of its (workload, K): max |diff| relative to max |C|.
 """
 import argparse
 import json
@@ -24,6 +26,9 @@ def main():
     ap.add_argument("--tasks", default="0,256,512,1024")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--rmat-scale", type=float, default=0.5)
+    ap.add_argument("--variants", default="0,2", help="GESPMM_VARIANT values; -1 = the library's automatic choice")
+    ap.add_argument("--valued", default="1,0")
+    ap.add_argument("--ref", action="store_true", help="also time the reference's spmm_test2<float> (oracle/_ref)")
     args = ap.parse_args()
     entry.load_package()
     from gespmm_b200 import graphs
@@ -38,10 +43,11 @@ def main():
             B = graphs.cli_dense(M, K, seed=1, device=dev)
             flops = 2.0 * nnz * K
             first = None
-            for valued in (True, False):
-                for variant in (0, 2):
+            for valued in (bool(int(x)) for x in args.valued.split(",")):
+                for variant in (int(x) for x in args.variants.split(",")):
                     for task in args.tasks.split(","):
                         os.environ["GESPMM_VARIANT"], os.environ["GESPMM_TASK"] = str(variant), task
+                        torch.cuda.empty_cache()
                         run = (lambda: spmm.csr_spmm(rowptr, colind, val, B)) if valued else (lambda: spmm.csr_spmm_no_edge_value(rowptr, colind, B))
                         for _ in range(3):
                             C = run()
@@ -60,6 +66,14 @@ def main():
                                           "ms": round(ms, 4), "gflops": round(flops / ms / 1e6, 1), "gather_gbs": round(nnz * K * 4 / ms / 1e6, 1),
                                           "max_rel_diff_vs_ring": rel}), flush=True)
                         del C
+            if args.ref and M * K < 2**31:
+                L = entry.load_oracle().ref_cli_kernels()
+                Cr = torch.empty(M, K, device=dev)
+                rms = L.ref_spmm_time_ms(2, 8, M, K, rowptr.data_ptr(), colind.data_ptr(), val.data_ptr(), B.data_ptr(), Cr.data_ptr(), 2, args.iters)
+                rel = float((Cr - first).abs().max() / first.abs().max().clamp_min(1e-30))
+                print(json.dumps({"workload": wl, "M": M, "nnz": nnz, "K": K, "reference_kernel": "spmm_test2<float> tile_row 8", "ms": round(rms, 4),
+                                  "gflops": round(flops / rms / 1e6, 1), "max_rel_diff_vs_ring": rel}), flush=True)
+                del Cr
             del B, first
         del rowptr, colind, val
         torch.cuda.empty_cache()
