@@ -72,10 +72,15 @@ const char *gespmm_error_string(int code);
  *   C                         fp32, device, row-major, row stride ldc >= K.  Every element of
  *                             C[0:M, 0:K] is written (empty rows -> 0), like the reference.
  * Per output element the products are accumulated in CSR order into one fp32 accumulator
- * starting from 0 (FFMA for valued, FADD for unvalued) -- the reference kernels' order --
- * except for rows longer than GESPMM_LONG_ROW nonzeros, which are summed in 8 contiguous
- * segments (one per warp of a CTA) combined in fixed order (deterministic, differs from the reference only by fp32
- * re-association).
+ * starting from 0 (FFMA for valued, FADD for unvalued) -- the reference kernels' order, hence
+ * bit-identical results -- with two exceptions, both deterministic and differing from the reference
+ * by fp32 re-association only (see gespmm_row_sum_is_sequential below):
+ *   - rows longer than GESPMM_LONG_ROW nonzeros are summed in 8 contiguous segments (one per warp
+ *     of a CTA; 64 segments across a thread-block cluster from 32768 nonzeros) combined in fixed order;
+ *   - for K <= 64 (K % 4 == 0, aligned operands) a warp gathers 2 / 4 / 8 B rows per instruction and
+ *     keeps one partial sum per lane group (nonzeros p, p + NG, p + 2 NG, ... of the row), added in a
+ *     fixed butterfly order at the row end.  GESPMM_VARIANT=0 in the environment selects the
+ *     sequential walker for every K (1.5-4.7x slower at K <= 32 on B200).
  * N is used for argument checking only (colind values are trusted, like the reference).
  */
 int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
