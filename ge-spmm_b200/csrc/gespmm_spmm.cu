@@ -61,8 +61,10 @@
 //
 // Column mapping
 //   Lane l owns, for v < V, the float4 at column ((v*32 + l) * 4) of the current panel
-//   (panel = 128*V columns; blockIdx.y walks panels for K > 512).  One warp-wide copy
-//   therefore moves 512 contiguous bytes of a B row.
+//   (panel = 128*V columns; blockIdx.y walks the panels one after the other).  One warp-wide
+//   copy therefore moves 512 contiguous bytes of a B row.  V = 1 for B in local memory (a pass
+//   over a 128-column panel gathers from an N x 512-byte slice of B: the smallest L2 footprint),
+//   up to 4 for a sharded B.  K <= 64: see WalkerSub (several nonzeros per warp-wide copy).
 
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -1058,7 +1060,18 @@ int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr
     }
     const int W = vec4 ? 4 : 1;
     const int packs = (int)((K + 32 * W - 1) / (32 * W));
-    const int V = packs >= 4 ? 4 : packs;
+    // Packs per lane = panel width / (32 W) columns; blockIdx.y walks the panels one after the other, each
+    // pass re-reading the CSR arrays.  With B in local memory a pass over a 128-column panel (V = 1) gathers
+    // from an N x 512-byte slice of B, a quarter of the L2 footprint of a 512-column pass, and that outweighs
+    // the extra colind reads on every shape measured (K = 256 / 512: Reddit 1.13x / 1.34x, R-MAT 1.14x / 1.19x,
+    // cit-Patents 1.10x / 1.17x, ogbn-products 1.04x; profiles/r01_sweep_panel.txt).  Sharded B keeps wide
+    // panels (one 2 KB request per remote row instead of four).  GESPMM_PANEL_V (1..4) overrides.
+    const int max_v = packs >= 4 ? 4 : packs;
+    int V = (vec4 && parts == 0) ? 1 : max_v;
+    {
+        const int forced_v = env_int("GESPMM_PANEL_V", 0);
+        if (forced_v >= 1 && forced_v <= max_v) V = forced_v;
+    }
     const bool masked = (K % (32 * W * V)) != 0;  // some lanes' packs fall beyond K
 
     // Task window (keys per task).  A task's start-up (row search, first rowptr / colind fetch) is

@@ -1,7 +1,7 @@
 #!/bin/bash
 # One bounded GPU session (run through gpurun from the repo root): every step under its own timeout, most
 # important first, everything into gpurun_out/.  Usage: bash scripts/gpu_session.sh [steps...]
-#   steps: subwarp sweep ksweep suite seq auto64 bench smoke sanitize ncu   (default: all, in that order)
+#   steps: subwarp sweep ksweep suite seq auto64 bench smoke sanitize launches ncu128 ncu   (default: all, in that order)
 cd "$(dirname "$0")/.." || exit 1
 O=gpurun_out
 mkdir -p $O
@@ -51,6 +51,14 @@ PY
             --K 16,32,64 --iters 2 --validate --out $O/sanitize.csv 2>&1 | grep -E "SUMMARY|validate|WA|Error|error" | head -12 >> $O/sanitize_subwarp.txt
       done
       note "sanitize done" ;;
+    launches) # launch list of the bench command (per-launch times are cold-cache and serialised: compare shares)
+      timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv \
+          python bench.py --steps 3 --warmup 3 --no-cpu > $O/launches_bench.log 2>&1; note "launches rc=$?"
+      python scripts/summarize_launches.py $O/launches.csv > $O/launches_summary.txt 2>&1 ;;
+    ncu128)   # one full capture of the dominant kernel of the bench command (cit-Patents shape, K = 128)
+      timeout 400 ncu --set full --clock-control none --import-source on -k regex:spmm_flat_kernel --launch-skip 3 -c 1 \
+          -f -o $O/ncu_citpatents_K128 python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-ref-kernel > $O/ncu128.log 2>&1
+      note "ncu128 rc=$?" ;;
     ncu)      # one full capture of each walker's kernel A on the ogbn-products shape, K = 32
       for v in 2 0; do
         GESPMM_VARIANT=$v timeout 400 ncu --set full --clock-control none --import-source on -k regex:spmm_flat_kernel --launch-skip 3 -c 1 \
