@@ -681,6 +681,171 @@ struct WalkerSub {
 };
 
 // =================================================================================================
+// Row-parallel narrow walker (K <= 64): the lane groups own DISJOINT ROWS, sequential order kept.
+// =================================================================================================
+// Same lane layout and ring as WalkerSub, but instead of dealing consecutive nonzeros of one row to
+// the NG groups (which re-associates the row's sum), the rows of the current run (<= 32 rows whose
+// nonzeros are contiguous) are dealt to the groups as NG contiguous blocks, balanced on nonzeros by
+// the midpoint of each row's range.  Every group then walks its own rows' nonzeros in CSR order,
+// LPR = 32 / NG nonzeros per chunk, all groups in lock-step: step k of a chunk copies / reads back /
+// accumulates the k-th nonzero of each group's chunk.  One accumulator per output element, products
+// added in CSR order -- bit-identical to the reference like the ring walker -- and a row end is a
+// predicated store by the group that owns the row: no cross-group combine.  The price is balance: a
+// run takes as many chunks as its longest group needs (measured on the generators' degree
+// distributions: 95-97 % of ideal at NG = 2, 82-92 % at NG = 4, 53-73 % at NG = 8).
+// Rows only; kernel B (long rows, re-associated anyway) pairs it with WalkerSub.
+template <int NG, bool VALUED, bool MAXR = false>
+struct WalkerRows {
+    using P = Pack<true>;
+    using T = float4;
+    using R = Reduce<P, VALUED, MAXR>;
+    static_assert(NG == 2 || NG == 4 || NG == 8, "2, 4 or 8 row blocks per warp");
+    static constexpr int LPR = 32 / NG;             // lanes per group = nonzeros per group per chunk
+    static constexpr int QS = LPR < 8 ? LPR : 8;    // steps per ring stage
+    static constexpr int SPC = LPR / QS;            // stages per chunk (1 or 2)
+    static constexpr int UB = 4;                    // steps read back from the ring per LDS batch
+    static constexpr int kStageBytes = QS * 512;
+    static constexpr int kRingBytes = 2 * kStageBytes;
+    static constexpr int kPanel = LPR * 4;
+    static constexpr unsigned kGroupOnes = LPR == 4 ? 0x11111111u : (LPR == 8 ? 0x01010101u : 0x00010001u);  // bit 0 of every group's field
+    static_assert(QS % UB == 0 && LPR % QS == 0, "bad stage shape");
+
+    float init_v;
+    const int *__restrict__ colind;
+    const float *__restrict__ val;
+    const char *__restrict__ Bl;
+    float *__restrict__ Cl;
+    unsigned ldb_bytes;
+    int ldc;
+    int lane, g, sl;              // group and position inside the group
+    bool active;                  // this lane's 4 columns lie inside K
+    unsigned ring;
+
+    __device__ __forceinline__ T start() const { return R::start(init_v); }
+
+    __device__ __forceinline__ void init(const Operands &o, int /*panel*/, int K, int ln, unsigned ring_base) {
+        lane = ln; g = ln / LPR; sl = ln % LPR;
+        const int col0 = sl * 4;
+        active = col0 < K;
+        colind = o.colind; val = o.val; Bl = reinterpret_cast<const char *>(o.B + col0); Cl = o.C + col0;
+        ldb_bytes = (unsigned)o.ldb * 4u; ldc = o.ldc;
+        ring = ring_base + ln * 16;
+        init_v = o.init;
+    }
+
+    // kernel A's empty rows: one group writes the row
+    __device__ __forceinline__ void store_row(int row, const T (&acc)[1]) const {
+        if (g == 0 && active) P::stcs(Cl + (long long)row * ldc, acc[0]);
+    }
+
+    // copies for steps [k0, k0 + QS) of a chunk in which my group still has n nonzeros; one commit group
+    __device__ __forceinline__ void issue(int cols, int k0, int n, unsigned slot) const {
+#pragma unroll
+        for (int i0 = 0; i0 < QS; i0 += UB) {
+            const char *bp[UB];
+#pragma unroll
+            for (int i = 0; i < UB; i++) {
+                const int c = __shfl_sync(kFull, cols, k0 + i0 + i, LPR);  // the (k0+i0+i)-th lane of my group
+                bp[i] = Bl + (unsigned long long)(unsigned)c * ldb_bytes;
+            }
+#pragma unroll
+            for (int i = 0; i < UB; i++)
+                if (active && k0 + i0 + i < n) cp_async16<0>(ring + slot + (i0 + i) * 512, bp[i]);
+        }
+        cp_async_commit();
+    }
+
+    // steps [k0, k0 + QS) of the chunk: n = my group's nonzeros left, nmin = the least over the groups
+    __device__ __forceinline__ void consume(float vals, int k0, int n, int nmin, unsigned endmask, T &acc, unsigned &left,
+                                            int rb, unsigned slot) const {
+#pragma unroll
+        for (int i0 = 0; i0 < QS; i0 += UB) {
+            T b[UB];
+            float a[UB];
+#pragma unroll
+            for (int i = 0; i < UB; i++) {
+                a[i] = VALUED ? __shfl_sync(kFull, vals, k0 + i0 + i, LPR) : 1.f;
+                b[i] = lds128(ring + slot + (i0 + i) * 512);  // stale bytes where nothing was copied: never added
+            }
+            const unsigned ends = endmask & ((kGroupOnes * ((1u << UB) - 1u)) << (k0 + i0));  // any group, these UB steps
+            if (ends == 0u && nmin >= k0 + i0 + UB) {  // warp-uniform: every group is live and no row ends
+#pragma unroll
+                for (int i = 0; i < UB; i++) R::step(acc, a[i], b[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < UB; i++) {
+                    const int k = k0 + i0 + i;
+                    if (k < n) R::step(acc, a[i], b[i]);
+                    if ((endmask >> (g * LPR + k)) & 1u) {  // my group's current row ends with this nonzero
+                        if (active) P::stcs(Cl + (long long)(rb + __ffs(left) - 1) * ldc, acc);
+                        left &= left - 1;
+                        acc = start();
+                    }
+                }
+            }
+        }
+    }
+
+    // Rows `rows` (bits = row - rb; non-empty, their nonzeros are exactly [s, e), lane r holds row r's end).
+    __device__ __forceinline__ void stream(int s, int e, T (&accv)[1], int my_end, unsigned rows, int rb) const {
+        T acc = accv[0];
+        const bool my_row = (rows >> lane) & 1u;
+        // the row I hold starts where the previous row of the run ends
+        const unsigned below = rows & low_bits(lane);
+        const int prev_end = __shfl_sync(kFull, my_end, below ? 31 - __clz(below) : 0);
+        const int my_start = below ? prev_end : s;
+        // its block: by the midpoint of its nonzero range inside [s, e)
+        int grp = 0;
+        if (my_row) grp = min(NG - 1, ((my_start + my_end - 2 * s) * NG) / (2 * (e - s)));
+        unsigned mine = 0;  // the rows of my group
+#pragma unroll
+        for (int q = 0; q < NG; q++) {
+            const unsigned m = __ballot_sync(kFull, my_row && grp == q);
+            if (q == g) mine = m;
+        }
+        int gs = __shfl_sync(kFull, my_start, mine ? __ffs(mine) - 1 : 0);
+        int ge = __shfl_sync(kFull, my_end, mine ? 31 - __clz(mine) : 0);
+        if (!mine) gs = ge = 0;
+        const int row_gs = __shfl_sync(kFull, gs, grp * LPR);  // where the stream of my ROW's group starts
+        const int maxlen = __reduce_max_sync(kFull, ge - gs);   // the run takes ceil(maxlen / LPR) chunks
+
+        unsigned left = mine;
+        int p = gs;
+        int ccol = 0, ncol = 0, fcol = 0;
+        float cval = 1.f, nval = 1.f;
+        if (p + sl < ge) {
+            ccol = __ldcs(colind + p + sl);
+            if (VALUED) cval = __ldcs(val + p + sl);
+        }
+        if (p + LPR + sl < ge) ncol = __ldcs(colind + p + LPR + sl);
+        unsigned slot = 0;
+        issue(ccol, 0, ge - p, 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < maxlen; c0 += LPR, p += LPR) {
+            if (p + 2 * LPR + sl < ge) fcol = __ldcs(colind + p + 2 * LPR + sl);
+            if (VALUED && p + LPR + sl < ge) nval = __ldcs(val + p + LPR + sl);
+            // row ends of every group inside this chunk: one LPR-bit field per group
+            const unsigned rel = (unsigned)(my_end - 1 - (row_gs + c0));
+            const unsigned endmask = __reduce_or_sync(kFull, (my_row && rel < (unsigned)LPR) ? (1u << (grp * LPR + rel)) : 0u);
+            const int n = ge - p;  // my group's nonzeros from this chunk on (<= 0: done)
+            const int nmin = __reduce_min_sync(kFull, n);
+#pragma unroll
+            for (int j = 0; j < SPC; j++) {
+                if (j * QS >= maxlen - c0) break;  // only in the last chunk, where nothing is in flight past it
+                const bool nxt = j + 1 >= SPC;
+                issue(nxt ? ncol : ccol, nxt ? 0 : (j + 1) * QS, nxt ? n - LPR : n, slot ^ kStageBytes);
+                cp_async_wait<1>();
+                consume(cval, j * QS, n, nmin, endmask, acc, left, rb, slot);
+                slot ^= kStageBytes;
+            }
+            ccol = ncol; ncol = fcol; cval = nval;
+        }
+        cp_async_wait<0>();
+        accv[0] = acc;
+    }
+};
+
+// =================================================================================================
 // Kernel A: short rows.  One warp per CTA, one task per CTA.
 // =================================================================================================
 template <class WK, int V, bool VEC4, int MINB>
@@ -906,15 +1071,15 @@ Side *side_for_current_device()
     return &sd;
 }
 
-template <class WK, int V, bool VEC4, int MINB>
+template <class WK, int V, bool VEC4, int MINB, class WKB = WK>
 cudaError_t launch(const Args &a)
 {
     const unsigned panels = (unsigned)((a.K + WK::kPanel - 1) / WK::kPanel);
     const bool has_b = a.nnz > a.long_row;
     Side *sd = (has_b && a.overlap) ? side_for_current_device() : nullptr;
     if (has_b) {
-        constexpr int dynB = WK::kRingBytes * kLongWarps;
-        auto kernB = spmm_long_kernel<WK, V, VEC4>;
+        constexpr int dynB = WKB::kRingBytes * kLongWarps;
+        auto kernB = spmm_long_kernel<WKB, V, VEC4>;
         if (dynB > 0) {  // static + dynamic shared memory exceeds the 48 KB default: opt in, once per device
             static bool done[kMaxDevices] = {};
             int dev = 0;
@@ -979,11 +1144,28 @@ cudaError_t dispatch_sub(int K, const Args &a)
     return launch<WalkerSub<8, VALUED, MAXR>, 1, true, 24>(a);
 }
 
+// The row-parallel narrow walker (sequential order); long rows go to kernel B with the sub-warp walker.
+template <bool VALUED, bool MAXR>
+cudaError_t dispatch_rows(int K, const Args &a)
+{
+    if (K > 32) return launch<WalkerRows<2, VALUED, MAXR>, 1, true, 24, WalkerSub<2, VALUED, MAXR>>(a);
+    if (K > 16) return launch<WalkerRows<4, VALUED, MAXR>, 1, true, 24, WalkerSub<4, VALUED, MAXR>>(a);
+    return launch<WalkerRows<8, VALUED, MAXR>, 1, true, 24, WalkerSub<8, VALUED, MAXR>>(a);
+}
+
 // Which walker sums the short rows of a product of width K on aligned operands.
 //   GESPMM_VARIANT unset / < 0 : automatic -- the sub-warp walker for K <= GESPMM_SUBWARP_MAX_K, else the ring walker
 //   0 : ring walker (the reference's sequential order for every K)   1 : register-staged walker (comparisons)
 //   2 : sub-warp walker wherever it applies (K <= 64)
+//   4 : row-parallel narrow walker wherever it applies (K <= 64; sequential order)
 constexpr int kSubwarpMaxKDefault = 64;  // measured on B200 (profiles/r01_sweep_narrow.txt): 1.1-6x the ring walker at K <= 64
+//   GESPMM_SEQUENTIAL=1 : the fastest walker that keeps the reference's order for every K (= variant 4)
+int env_variant()
+{
+    if (env_int("GESPMM_SEQUENTIAL", 0) != 0) return 4;
+    return env_int("GESPMM_VARIANT", -1);
+}
+bool use_rows(int64_t K, int variant) { return variant == 4 && K <= 64 && K % 4 == 0; }
 bool use_subwarp(int64_t K, int variant)
 {
     if (K > 64 || K % 4 != 0) return false;
@@ -1082,15 +1264,16 @@ int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr
     // GESPMM_TASK / GESPMM_LONG / GESPMM_VARIANT / GESPMM_OVERLAP are tuning overrides (read per call).
     const int forced_task = env_int("GESPMM_TASK", 0);
     const int forced_long = env_int("GESPMM_LONG", 0);
-    const int variant = env_int("GESPMM_VARIANT", -1);
+    const int variant = env_variant();
     const bool sub = vec4 && parts == 0 && use_subwarp(K, variant);
+    const bool rows_walker = vec4 && parts == 0 && use_rows(K, variant);
     const long long total = nnz + M;
     const long long warps_per_wave = 148LL * 24;
     const double keys_per_row = (double)total / (double)M;
     long long tk = ((long long)(48.0 * sqrt(keys_per_row)) + 31) & ~31LL;
     // the sub-warp walker spends 1/NG of the instructions per nonzero, so a task's start-up weighs NG times more:
     // measured optima are 512 (cit-Patents shape) to 1024 (ogbn-products, R-MAT, Reddit shapes) at K = 16, 32
-    if (sub) tk *= (K > 32 ? 2 : (K > 16 ? 4 : 8));
+    if (sub || rows_walker) tk *= (K > 32 ? 2 : (K > 16 ? 4 : 8));
     const long long cap = (total / (8 * warps_per_wave)) & ~31LL;
     if (tk > cap) tk = cap;
     int task = (int)(tk < 32 ? 32 : (tk > kMaxTask ? kMaxTask : tk));
@@ -1104,7 +1287,10 @@ int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr
     a.overlap = env_int("GESPMM_OVERLAP", 1) != 0;
     a.op.init = init;
     cudaError_t err;
-    if (sub) {
+    if (rows_walker) {
+        if (max_reduce) err = val ? dispatch_rows<true, true>((int)K, a) : dispatch_rows<false, true>((int)K, a);
+        else err = val ? dispatch_rows<true, false>((int)K, a) : dispatch_rows<false, false>((int)K, a);
+    } else if (sub) {
         if (max_reduce) err = val ? dispatch_sub<true, true>((int)K, a) : dispatch_sub<false, true>((int)K, a);
         else err = val ? dispatch_sub<true, false>((int)K, a) : dispatch_sub<false, false>((int)K, a);
     } else if (max_reduce) {
@@ -1133,7 +1319,7 @@ extern "C" int gespmm_row_sum_is_sequential(int64_t K, int64_t row_nnz)
 {
     const int forced_long = env_int("GESPMM_LONG", 0);
     if (row_nnz > (forced_long >= kMinLong ? forced_long : GESPMM_LONG_ROW)) return 0;  // segmented (kernel B)
-    if (row_nnz > 1 && use_subwarp(K, env_int("GESPMM_VARIANT", -1))) return 0;       // per-group partial sums
+    if (row_nnz > 1 && use_subwarp(K, env_variant())) return 0;                         // per-group partial sums
     return 1;
 }
 

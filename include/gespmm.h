@@ -79,8 +79,9 @@ const char *gespmm_error_string(int code);
  *     of a CTA; 64 segments across a thread-block cluster from 32768 nonzeros) combined in fixed order;
  *   - for K <= 64 (K % 4 == 0, aligned operands) a warp gathers 2 / 4 / 8 B rows per instruction and
  *     keeps one partial sum per lane group (nonzeros p, p + NG, p + 2 NG, ... of the row), added in a
- *     fixed butterfly order at the row end.  GESPMM_VARIANT=0 in the environment selects the
- *     sequential walker for every K (1.5-4.7x slower at K <= 32 on B200).
+ *     fixed butterfly order at the row end.  GESPMM_SEQUENTIAL=1 in the environment selects, for
+ *     every K, the fastest walker that keeps the sequential order (for K <= 64: lane groups own
+ *     disjoint rows; 0.5-1.07x the default's speed on B200, 1.2-2.1x the plain one-row-per-gather walker).
  * N is used for argument checking only (colind values are trusted, like the reference).
  */
 int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,

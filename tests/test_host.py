@@ -91,7 +91,7 @@ def test_argument_validation_without_a_device(pkg):
 def test_row_sum_order_query(pkg, monkeypatch):
     """gespmm_row_sum_is_sequential is a pure function of (K, row length) and the tuning environment."""
     from gespmm_b200 import capi
-    for name in ("GESPMM_VARIANT", "GESPMM_SUBWARP_MAX_K", "GESPMM_LONG"):
+    for name in ("GESPMM_VARIANT", "GESPMM_SUBWARP_MAX_K", "GESPMM_LONG", "GESPMM_SEQUENTIAL"):
         monkeypatch.delenv(name, raising=False)
     for K in (1, 4, 32, 64, 100, 128, 512, 4096):
         assert capi.row_sum_is_sequential(K, 0) and capi.row_sum_is_sequential(K, 1)
@@ -103,6 +103,12 @@ def test_row_sum_order_query(pkg, monkeypatch):
     monkeypatch.setenv("GESPMM_VARIANT", "2")  # the sub-warp walker wherever it applies: K <= 64, K % 4 == 0
     assert not any(capi.row_sum_is_sequential(K, 2) for K in (4, 16, 32, 48, 64))
     assert all(capi.row_sum_is_sequential(K, 2) for K in (3, 30, 65, 68, 128))
+    monkeypatch.setenv("GESPMM_VARIANT", "4")  # the row-parallel narrow walker: sequential again
+    assert all(capi.row_sum_is_sequential(K, capi.LONG_ROW) for K in (4, 16, 32, 48, 64, 128))
+    monkeypatch.setenv("GESPMM_VARIANT", "2")
+    monkeypatch.setenv("GESPMM_SEQUENTIAL", "1")  # wins over GESPMM_VARIANT
+    assert all(capi.row_sum_is_sequential(K, capi.LONG_ROW) for K in (4, 16, 32, 48, 64, 128))
+    monkeypatch.delenv("GESPMM_SEQUENTIAL")
     monkeypatch.delenv("GESPMM_VARIANT")
     monkeypatch.setenv("GESPMM_SUBWARP_MAX_K", "32")
     assert not capi.row_sum_is_sequential(32, 2) and capi.row_sum_is_sequential(64, 2)

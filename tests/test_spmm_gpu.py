@@ -234,6 +234,40 @@ def test_subwarp_walker_for_narrow_B(spmm, dev, oracle, pkg, monkeypatch, K):
     assert np.array_equal(C[short], want[short])
 
 
+@pytest.mark.parametrize("K", [4, 8, 16, 24, 32, 36, 48, 64])
+def test_row_parallel_walker_for_narrow_B_is_sequential(spmm, dev, oracle, pkg, monkeypatch, K):
+    """GESPMM_VARIANT=4: the lane groups own disjoint rows, each summed in CSR order -- bit-identical to the oracle
+    (real-valued operands) on every row up to GESPMM_LONG_ROW, whatever the balance of the 32-row runs: empty rows,
+    single-row runs between long rows, rows much longer than their neighbours; max-reduce bit-identical everywhere."""
+    from gespmm_b200 import capi
+    monkeypatch.setenv("GESPMM_VARIANT", "4")
+    assert capi.row_sum_is_sequential(K, LONG) and not capi.row_sum_is_sequential(K, LONG + 1)
+    rng = np.random.default_rng(700 + K)
+    M, N = 2600, 3000
+    deg = rng.integers(0, 9, M)
+    deg[rng.random(M) < 0.3] = 0
+    deg[[5, 6, 7, 900, 2599]] = [40000, 4097, 4100, 3000, 33000]   # row 6 sits alone between two long rows
+    deg[1000:1100] = rng.integers(20, 400, 100)
+    deg[1500:1532] = 0
+    deg[1510] = 1
+    rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    nnz = int(rowptr[-1])
+    colind = rng.integers(0, N, nnz).astype(np.int32)
+    Bf = rng.standard_normal((N, K)).astype(np.float32)
+    vf = rng.standard_normal(nnz).astype(np.float32)
+    for v in (None, vf):
+        C1 = _run(spmm, dev, rowptr, colind, v, Bf)
+        assert _check(oracle, rowptr, colind, v, Bf, C1) == 4
+        assert torch.equal(C1, _run(spmm, dev, rowptr, colind, v, Bf)), "must be deterministic"
+    rp, ci, v, Bd = (torch.as_tensor(x, device=dev) for x in (rowptr, colind, vf, Bf))
+    for vv in (None, v):
+        C = torch.full((M, K), float("nan"), device=dev)
+        capi.csr_spmm_max_f32(M, N, K, nnz, rp.data_ptr(), ci.data_ptr(), None if vv is None else vv.data_ptr(), Bd.data_ptr(), K,
+                              C.data_ptr(), K, -10000.0, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(C.cpu().numpy(), oracle.spmm_max(rowptr, colind, None if vv is None else vf, Bf, init=-10000.0))
+
+
 def test_skewed_rmat_graph(spmm, dev, oracle, pkg):
     from gespmm_b200 import graphs
     rowptr, colind = graphs.rmat(N=200_000, nnz=4_000_000, seed=4)
