@@ -20,6 +20,7 @@ LONG_ROW = 4096
 SYMBOLS = (
     "gespmm_version", "gespmm_error_string", "gespmm_csr_spmm_f32", "gespmm_csr_spmm_f32_host", "gespmm_csr_spmm_f32_bparts", "gespmm_csr_spmm_max_f32", "gespmm_row_sum_is_sequential", "gespmm_enable_peer_access", "gespmm_ipc_open", "gespmm_ipc_close", "gespmm_ipc_alloc", "gespmm_ipc_free",
     "gespmm_csr2csc_workspace_bytes", "gespmm_csr2csc_f32", "gespmm_read_mtx", "gespmm_free_host",
+    "gespmm_write_csr", "gespmm_read_csr", "gespmm_read_mtx_cached",
 )
 
 _lib = None
@@ -73,6 +74,14 @@ def lib():
         L.gespmm_read_mtx.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                       ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(p), ctypes.POINTER(p),
                                       ctypes.POINTER(p)]
+        outs = [ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64),
+                ctypes.POINTER(p), ctypes.POINTER(p), ctypes.POINTER(p)]
+        L.gespmm_write_csr.restype = ctypes.c_int
+        L.gespmm_write_csr.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32, i64, p, p, p]
+        L.gespmm_read_csr.restype = ctypes.c_int
+        L.gespmm_read_csr.argtypes = [ctypes.c_char_p] + outs
+        L.gespmm_read_mtx_cached.restype = ctypes.c_int
+        L.gespmm_read_mtx_cached.argtypes = [ctypes.c_char_p, ctypes.c_char_p] + outs + [ctypes.POINTER(ctypes.c_int)]
         L.gespmm_free_host.restype = None
         L.gespmm_free_host.argtypes = [p]
         _lib = L
@@ -167,15 +176,14 @@ def csr_spmm_host(rowptr, colind, val, B, device=0):
     return C
 
 
-def read_mtx(path):
-    """MatrixMarket file -> (nrows, ncols, rowptr, colind, val) as numpy arrays (readMtx post-conditions)."""
+def _take_csr(call, what):
+    """Run a reader entry point and copy its malloc'ed arrays into numpy arrays."""
     L = lib()
     nr, nc, nnz = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()
     rp, ci, vv = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
-    rc = L.gespmm_read_mtx(os.fsencode(path), ctypes.byref(nr), ctypes.byref(nc), ctypes.byref(nnz),
-                           ctypes.byref(rp), ctypes.byref(ci), ctypes.byref(vv))
+    rc = call(ctypes.byref(nr), ctypes.byref(nc), ctypes.byref(nnz), ctypes.byref(rp), ctypes.byref(ci), ctypes.byref(vv))
     if rc != OK:
-        raise GespmmError(rc, "gespmm_read_mtx(%s)" % path)
+        raise GespmmError(rc, what)
     try:
         n = nnz.value
         rowptr = np.ctypeslib.as_array(ctypes.cast(rp, ctypes.POINTER(ctypes.c_int32)), (nr.value + 1,)).copy()
@@ -187,3 +195,37 @@ def read_mtx(path):
     finally:
         L.gespmm_free_host(rp); L.gespmm_free_host(ci); L.gespmm_free_host(vv)
     return nr.value, nc.value, rowptr, colind, val
+
+
+def read_mtx(path, cache=None):
+    """MatrixMarket file -> (nrows, ncols, rowptr, colind, val) as numpy arrays (readMtx post-conditions).
+    ``cache``: None = always parse; True = keep / use the binary image "<path>.gespmm-csr"; a path = that image."""
+    L = lib()
+    if cache is None or cache is False:
+        return _take_csr(lambda *o: L.gespmm_read_mtx(os.fsencode(path), *o), "gespmm_read_mtx(%s)" % path)
+    image = None if cache is True else os.fsencode(cache)
+    return _take_csr(lambda *o: L.gespmm_read_mtx_cached(os.fsencode(path), image, *o, None), "gespmm_read_mtx_cached(%s)" % path)
+
+
+def read_mtx_cached(path, cache_path=None):
+    """Like read_mtx(path, cache=...) but also reports whether the image was used: (..., cache_hit)."""
+    L = lib()
+    hit = ctypes.c_int(0)
+    out = _take_csr(lambda *o: L.gespmm_read_mtx_cached(os.fsencode(path), None if cache_path is None else os.fsencode(cache_path),
+                                                       *o, ctypes.byref(hit)), "gespmm_read_mtx_cached(%s)" % path)
+    return out + (bool(hit.value),)
+
+
+def write_csr(path, nrows, ncols, rowptr, colind, val):
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+    colind = np.ascontiguousarray(colind, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float32)
+    rc = lib().gespmm_write_csr(os.fsencode(path), int(nrows), int(ncols), int(colind.shape[0]), rowptr.ctypes.data,
+                                colind.ctypes.data if colind.shape[0] else None, val.ctypes.data if val.shape[0] else None)
+    if rc != OK:
+        raise GespmmError(rc, "gespmm_write_csr(%s)" % path)
+
+
+def read_csr(path):
+    L = lib()
+    return _take_csr(lambda *o: L.gespmm_read_csr(os.fsencode(path), *o), "gespmm_read_csr(%s)" % path)

@@ -49,7 +49,7 @@ static void usage(const char *argv0)
 {
     fprintf(stderr,
             "usage: %s <file.mtx> [device_id] [--K a,b,c] [--iters n] [--seed s] [--valued] [--validate]\n"
-            "          [--baseline-lib libref_cli_kernels.so] [--json] [--out file] [--hbm-gbs peak]\n",
+            "          [--baseline-lib libref_cli_kernels.so] [--json] [--out file] [--hbm-gbs peak] [--cache]\n",
             argv0);
 }
 
@@ -61,6 +61,7 @@ int main(int argc, char **argv)
     unsigned seed = 1;
     bool validate = false, json = false, valued_kernel = true;  // the reference CLI times the valued kernel with A == 1
     bool unvalued = false;
+    bool cache = getenv("GESPMM_MTX_CACHE") != nullptr;  // keep / use the parsed CSR next to the file (<file>.gespmm-csr)
     double hbm_gbs = 8000.0;
     std::string out_path = "spmm_test_out.out", baseline_lib;
     std::vector<int> ks;
@@ -90,6 +91,7 @@ int main(int argc, char **argv)
         else if (a == "--baseline-lib") baseline_lib = need("--baseline-lib");
         else if (a == "--out") out_path = need("--out");
         else if (a == "--hbm-gbs") hbm_gbs = atof(need("--hbm-gbs"));
+        else if (a == "--cache") cache = true;
         else { usage(argv[0]); return 2; }
     }
     if (unvalued) valued_kernel = false;
@@ -107,7 +109,10 @@ int main(int argc, char **argv)
     int64_t nnz = 0;
     int32_t *rowptr = nullptr, *colind = nullptr;
     float *aval = nullptr;
-    int rc = gespmm_read_mtx(mtx, &M, &N, &nnz, &rowptr, &colind, &aval);
+    int cache_hit = 0;
+    int rc = cache ? gespmm_read_mtx_cached(mtx, nullptr, &M, &N, &nnz, &rowptr, &colind, &aval, &cache_hit)
+                   : gespmm_read_mtx(mtx, &M, &N, &nnz, &rowptr, &colind, &aval);
+    if (cache) fprintf(stderr, "[spmm_test] %s\n", cache_hit ? "loaded the binary CSR image next to the file" : "parsed the file, image written");
     if (rc != GESPMM_OK) {
         if (rc == GESPMM_ERR_IO) printf("File %s not found or not a MatrixMarket coordinate file", mtx);
         fprintf(stderr, "gespmm_read_mtx: %s\n", gespmm_error_string(rc));

@@ -22,6 +22,8 @@
  *                                  (pytorch-custom/spmm_kernel.cu:381-423, 460-477)
  *   gespmm_read_mtx / _free        readMtx<float> + COO->CSR of the CLI
  *                                  (util/util.hpp:286-333, spmm_test.cu:557-581)
+ *   gespmm_read_mtx_cached,        no reference counterpart: the parsed CSR kept as a binary image next
+ *   gespmm_write_csr / _read_csr   to the .mtx (the reference re-parses on every run, run_test.sh:5-10)
  *   gespmm_csr_spmm_f32_host       the CLI's cudaMalloc / cudaMemcpy block around the launch
  *                                  (spmm_test.cu:609-640)
  *   gespmm_csr_spmm_f32_bparts,    no reference counterpart (the reference is single-GPU): B left
@@ -178,6 +180,26 @@ int gespmm_csr2csc_f32(int64_t M, int64_t N, int64_t nnz,
 int gespmm_read_mtx(const char *path, int32_t *nrows, int32_t *ncols, int64_t *nnz,
                     int32_t **rowptr, int32_t **colind, float **val);
 void gespmm_free_host(void *p);
+
+/*
+ * Binary image of a host CSR (native endianness, tagged; 64-byte header, rowptr, colind, val) and
+ * gespmm_read_mtx through such an image: the reference re-parses its .mtx files on every run of the
+ * CLI (spmm_test.cu:537, run_test.sh:5-10); here the parsed arrays can be kept next to the file.
+ *   gespmm_write_csr / gespmm_read_csr   plain save / load (load checks the CSR invariants: monotone
+ *                                        rowptr, rowptr[nrows] == nnz, 0 <= colind < ncols).
+ *   gespmm_read_mtx_cached               `cache_path` (NULL: "<path>.gespmm-csr") is used when it exists
+ *                                        and records the .mtx's current size and modification time;
+ *                                        otherwise the .mtx is parsed and the image (re)written, best
+ *                                        effort -- a read-only directory does not fail the call.
+ *                                        *cache_hit (nullable) tells which happened.
+ * Arrays are malloc'ed by the library; release them with gespmm_free_host.
+ */
+int gespmm_write_csr(const char *path, int32_t nrows, int32_t ncols, int64_t nnz,
+                     const int32_t *rowptr, const int32_t *colind, const float *val);
+int gespmm_read_csr(const char *path, int32_t *nrows, int32_t *ncols, int64_t *nnz,
+                    int32_t **rowptr, int32_t **colind, float **val);
+int gespmm_read_mtx_cached(const char *path, const char *cache_path, int32_t *nrows, int32_t *ncols, int64_t *nnz,
+                           int32_t **rowptr, int32_t **colind, float **val, int *cache_hit);
 
 #ifdef __cplusplus
 }

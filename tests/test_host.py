@@ -184,6 +184,65 @@ def test_reader_roundtrip_through_writer_and_errors(pkg, tmp_path, golden_csr):
 
 # ---- operator surface ------------------------------------------------------------------------------
 
+def test_binary_csr_image_and_cached_reader(pkg, tmp_path, golden_csr):
+    """gespmm_write_csr / gespmm_read_csr round trip; gespmm_read_mtx_cached parses once, then loads the image, and
+    re-parses when the .mtx changes or the image is damaged; an unwritable image path does not fail the read."""
+    import shutil
+    import time
+    from gespmm_b200 import capi, graphs
+    rowptr, colind, shape = golden_csr("citeseer")   # has empty rows
+    val = np.arange(len(colind), dtype=np.float32) * 0.5 - 7
+    img = str(tmp_path / "a.csr")
+    capi.write_csr(img, shape[0], shape[1], rowptr, colind, val)
+    nr, nc, rp, ci, vv = capi.read_csr(img)
+    assert (nr, nc) == shape and np.array_equal(rp, rowptr) and np.array_equal(ci, colind) and np.array_equal(vv, val)
+    capi.write_csr(img, 3, 5, np.zeros(4, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float32))   # empty matrix
+    nr, nc, rp, ci, vv = capi.read_csr(img)
+    assert (nr, nc, rp.tolist(), len(ci), len(vv)) == (3, 5, [0, 0, 0, 0], 0, 0)
+    # damaged images are rejected, never half-trusted: truncation, bad magic, out-of-range column, non-monotone rowptr
+    capi.write_csr(img, shape[0], shape[1], rowptr, colind, val)
+    raw = open(img, "rb").read()
+    def rejected(data):
+        open(img, "wb").write(data)
+        with pytest.raises(capi.GespmmError):
+            capi.read_csr(img)
+    rejected(raw[:-4])
+    rejected(b"X" + raw[1:])
+    bad = bytearray(raw); off = 64 + 4 * (shape[0] + 1); bad[off:off + 4] = np.int32(shape[1]).tobytes(); rejected(bytes(bad))
+    bad = bytearray(raw); bad[64 + 4 * 10:64 + 4 * 11] = np.int32(2**30).tobytes(); rejected(bytes(bad))
+    with pytest.raises(capi.GespmmError):
+        capi.read_csr(str(tmp_path / "missing.csr"))
+
+    mtx = str(tmp_path / "g.mtx")
+    graphs.write_mtx(mtx, rowptr, colind, field="integer", values=np.arange(len(colind)) % 9 + 1)
+    want = capi.read_mtx(mtx)
+    out = capi.read_mtx_cached(mtx)
+    assert out[5] is False and os.path.exists(mtx + ".gespmm-csr")
+    assert all(np.array_equal(a, b) for a, b in zip(out[:5], want))
+    out = capi.read_mtx_cached(mtx)
+    assert out[5] is True and all(np.array_equal(a, b) for a, b in zip(out[:5], want))
+    assert all(np.array_equal(a, b) for a, b in zip(capi.read_mtx(mtx, cache=True), want))
+    # the .mtx changes (one entry fewer): the stale image must not be used
+    time.sleep(0.01)
+    graphs.write_mtx(mtx, rowptr[:-1], colind[:rowptr[-2]], N=shape[1])
+    want2 = capi.read_mtx(mtx)
+    out = capi.read_mtx_cached(mtx)
+    assert out[5] is False and out[0] == shape[0] - 1 and all(np.array_equal(a, b) for a, b in zip(out[:5], want2))
+    assert capi.read_mtx_cached(mtx)[5] is True
+    # a damaged image is ignored and rewritten
+    open(mtx + ".gespmm-csr", "r+b").write(b"garbage!")
+    out = capi.read_mtx_cached(mtx)
+    assert out[5] is False and all(np.array_equal(a, b) for a, b in zip(out[:5], want2))
+    assert capi.read_mtx_cached(mtx)[5] is True
+    # explicit image path; an unwritable one still reads
+    other = str(tmp_path / "elsewhere.bin")
+    assert capi.read_mtx_cached(mtx, other)[5] is False and capi.read_mtx_cached(mtx, other)[5] is True
+    out = capi.read_mtx_cached(mtx, str(tmp_path / "no" / "such" / "dir" / "x.bin"))
+    assert out[5] is False and all(np.array_equal(a, b) for a, b in zip(out[:5], want2))
+    with pytest.raises(capi.GespmmError):
+        capi.read_mtx_cached(str(tmp_path / "nope.mtx"))
+
+
 def test_operator_module_surface(pkg):
     from gespmm_b200 import op
     assert sorted(n for n in dir(op.spmm) if not n.startswith("_")) == ["csr2csc", "csr_spmm", "csr_spmm_no_edge_value"]
