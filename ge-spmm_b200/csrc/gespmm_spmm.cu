@@ -796,7 +796,7 @@ struct WalkerRows {
         const int my_start = below ? prev_end : s;
         // its block: by the midpoint of its nonzero range inside [s, e)
         int grp = 0;
-        if (my_row) grp = min(NG - 1, ((my_start + my_end - 2 * s) * NG) / (2 * (e - s)));
+        if (my_row) grp = min(NG - 1, (((my_start - s) + (my_end - s)) * NG) / (2 * (e - s)));  // offsets < 32 * long_row: no overflow
         unsigned mine = 0;  // the rows of my group
 #pragma unroll
         for (int q = 0; q < NG; q++) {
