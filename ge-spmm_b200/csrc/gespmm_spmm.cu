@@ -1120,6 +1120,15 @@ int env_int(const char *name, int dflt)
     return (s && *s) ? atoi(s) : dflt;
 }
 
+constexpr int kMaxLong = 1 << 20;  // largest accepted long-row threshold: a 32-row run then spans < 2^25 nonzeros
+// GESPMM_LONG: tuning override of GESPMM_LONG_ROW, clamped to [kMinLong, kMaxLong]
+int long_row_threshold()
+{
+    const int forced = env_int("GESPMM_LONG", 0);
+    if (forced < kMinLong) return GESPMM_LONG_ROW;
+    return forced > kMaxLong ? kMaxLong : forced;
+}
+
 // Default ring shape per V: (G rows per stage, MINB CTAs per SM); two stages.
 template <int V> struct Shape;
 template <> struct Shape<1> { static constexpr int G = 8, MINB = 24; };
@@ -1263,7 +1272,6 @@ int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr
     // capped so that the grid keeps at least ~8 waves of resident CTAs.
     // GESPMM_TASK / GESPMM_LONG / GESPMM_VARIANT / GESPMM_OVERLAP are tuning overrides (read per call).
     const int forced_task = env_int("GESPMM_TASK", 0);
-    const int forced_long = env_int("GESPMM_LONG", 0);
     const int variant = env_variant();
     const bool sub = vec4 && parts == 0 && use_subwarp(K, variant);
     const bool rows_walker = vec4 && parts == 0 && use_rows(K, variant);
@@ -1278,8 +1286,7 @@ int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr
     if (tk > cap) tk = cap;
     int task = (int)(tk < 32 ? 32 : (tk > kMaxTask ? kMaxTask : tk));
     if (forced_task >= 32 && forced_task <= kMaxTask) task = forced_task & ~31;
-    int long_row = GESPMM_LONG_ROW;
-    if (forced_long >= kMinLong) long_row = forced_long;
+    const int long_row = long_row_threshold();
 
     a.M = (int)M; a.K = (int)K; a.task = task; a.long_row = long_row; a.nnz = nnz; a.rowptr = rowptr;
     a.op.colind = colind; a.op.val = val; a.op.B = B; a.op.C = C; a.op.ldb = (int)ldb; a.op.ldc = (int)ldc;
@@ -1317,8 +1324,7 @@ extern "C" int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
 
 extern "C" int gespmm_row_sum_is_sequential(int64_t K, int64_t row_nnz)
 {
-    const int forced_long = env_int("GESPMM_LONG", 0);
-    if (row_nnz > (forced_long >= kMinLong ? forced_long : GESPMM_LONG_ROW)) return 0;  // segmented (kernel B)
+    if (row_nnz > long_row_threshold()) return 0;  // segmented (kernel B)
     if (row_nnz > 1 && use_subwarp(K, env_variant())) return 0;                         // per-group partial sums
     return 1;
 }
