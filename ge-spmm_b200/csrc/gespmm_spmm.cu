@@ -36,6 +36,13 @@
 //   in flight out of ~200 KB of rings), not by registers.  Unaligned operands / K % 4 != 0
 //   take the register variant (scalar loads, U rows in flight per warp).
 //
+// Narrow B (K <= 64, K % 4 == 0)
+//   A B row then fills only 32/NG lanes' 16-byte slices (NG = 2 / 4 / 8 for K <= 64 / 32 / 16), so the warp is
+//   split into NG lane groups and every copy / read-back instruction serves NG nonzeros at once:
+//   WalkerSub (default) deals consecutive nonzeros of the flat stream to the groups and adds the groups' partial
+//   sums at each row end (re-associated, deterministic); WalkerRows (GESPMM_SEQUENTIAL=1) deals whole rows to the
+//   groups and keeps the sequential order.  1.1-4.8x / 1.2-2.1x the ring walker at these widths.
+//
 // Reductions
 //   sum (the hot path) or max (gespmm_csr_spmm_max_f32: the reference's DGL patch,
 //   dgl-custom/binary_reduce_max.cu:18-168, `acc > x ? acc : x` from a caller-given start value).
