@@ -20,7 +20,7 @@ LONG_ROW = 4096
 SYMBOLS = (
     "gespmm_version", "gespmm_error_string", "gespmm_csr_spmm_f32", "gespmm_csr_spmm_f32_host", "gespmm_csr_spmm_f32_bparts", "gespmm_csr_spmm_max_f32", "gespmm_row_sum_is_sequential", "gespmm_enable_peer_access", "gespmm_ipc_open", "gespmm_ipc_close", "gespmm_ipc_alloc", "gespmm_ipc_free",
     "gespmm_csr2csc_workspace_bytes", "gespmm_csr2csc_f32", "gespmm_read_mtx", "gespmm_free_host",
-    "gespmm_write_csr", "gespmm_read_csr", "gespmm_read_mtx_cached",
+    "gespmm_write_csr", "gespmm_read_csr", "gespmm_read_mtx_cached", "gespmm_write_mtx",
 )
 
 _lib = None
@@ -78,6 +78,8 @@ def lib():
                 ctypes.POINTER(p), ctypes.POINTER(p), ctypes.POINTER(p)]
         L.gespmm_write_csr.restype = ctypes.c_int
         L.gespmm_write_csr.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32, i64, p, p, p]
+        L.gespmm_write_mtx.restype = ctypes.c_int
+        L.gespmm_write_mtx.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32, i64, p, p, p]
         L.gespmm_read_csr.restype = ctypes.c_int
         L.gespmm_read_csr.argtypes = [ctypes.c_char_p] + outs
         L.gespmm_read_mtx_cached.restype = ctypes.c_int
@@ -224,6 +226,18 @@ def write_csr(path, nrows, ncols, rowptr, colind, val):
                                 colind.ctypes.data if colind.shape[0] else None, val.ctypes.data if val.shape[0] else None)
     if rc != OK:
         raise GespmmError(rc, "gespmm_write_csr(%s)" % path)
+
+
+def write_mtx(path, nrows, ncols, rowptr, colind, val=None):
+    """CSR -> `general` MatrixMarket coordinate file (pattern if val is None, else real)."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+    colind = np.ascontiguousarray(colind, dtype=np.int32)
+    if val is not None:
+        val = np.ascontiguousarray(val, dtype=np.float32)
+    rc = lib().gespmm_write_mtx(os.fsencode(path), int(nrows), int(ncols), int(colind.shape[0]), rowptr.ctypes.data,
+                                colind.ctypes.data if colind.shape[0] else None, None if val is None else val.ctypes.data)
+    if rc != OK:
+        raise GespmmError(rc, "gespmm_write_mtx(%s)" % path)
 
 
 def read_csr(path):

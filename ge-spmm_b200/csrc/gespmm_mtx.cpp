@@ -411,3 +411,77 @@ extern "C" int gespmm_read_mtx_cached(const char *path, const char *cache_path, 
     (void)write_csr_image(image.c_str(), *nrows, *ncols, *nnz_out, *rowptr_out, *colind_out, *val_out, src_bytes, src_mtime);
     return GESPMM_OK;
 }
+
+// =================================================================================================
+// CSR -> MatrixMarket coordinate file (general; pattern when val is NULL, real otherwise).
+// =================================================================================================
+// The inverse of gespmm_read_mtx for `general` files: what the benchmarks use to put a synthetic graph in
+// front of the CLI (the reference's data/conv.c rewrites .mtx files with fprintf, one entry per call).
+// Rows are formatted by all host threads into per-slice buffers that are written in order.
+namespace {
+
+inline char *put_uint(char *p, uint32_t v)
+{
+    char tmp[10];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
+}  // namespace
+
+extern "C" int gespmm_write_mtx(const char *path, int32_t nrows, int32_t ncols, int64_t nnz, const int32_t *rowptr,
+                                const int32_t *colind, const float *val)
+{
+    if (!path || nrows < 0 || ncols < 0 || nnz < 0 || !rowptr || (nnz > 0 && !colind)) return GESPMM_ERR_INVALID_ARG;
+    if (rowptr[0] != 0 || rowptr[nrows] != nnz) return GESPMM_ERR_INVALID_ARG;
+    FILE *f = fopen(path, "wb");
+    if (!f) return GESPMM_ERR_IO;
+    fprintf(f, "%%%%MatrixMarket matrix coordinate %s general\n%%\n%d %d %lld\n", val ? "real" : "pattern", nrows, ncols,
+            (long long)nnz);
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (nthreads == 0) nthreads = 1;
+    if (nthreads > 8) nthreads = 8;
+    if (nnz < (1 << 20)) nthreads = 1;
+    // slices of rows with about equal numbers of entries, formatted in parallel, written in order
+    const int64_t per_round = (int64_t)4 << 20;  // entries per thread and round: bounds the buffers to ~130 MB per thread
+    bool ok = true;
+    int32_t row = 0;
+    while (row < nrows && ok) {
+        std::vector<int32_t> cut(nthreads + 1, nrows);
+        cut[0] = row;
+        for (unsigned t = 1; t <= nthreads; t++) {
+            const int64_t target = (int64_t)rowptr[cut[t - 1]] + per_round;
+            const int32_t *it = std::upper_bound(rowptr + cut[t - 1], rowptr + nrows + 1, (int32_t)std::min<int64_t>(target, INT32_MAX));
+            int32_t r = (int32_t)(it - rowptr) - 1;           // last row whose start is <= target
+            if (r <= cut[t - 1]) r = cut[t - 1] + 1;          // always advance (a single huge row)
+            cut[t] = r > nrows ? nrows : r;
+        }
+        std::vector<std::vector<char>> out(nthreads);
+        auto work = [&](unsigned t) {
+            const int32_t r0 = cut[t], r1 = cut[t + 1];
+            if (r0 >= r1) return;
+            std::vector<char> &b = out[t];
+            b.resize((size_t)(rowptr[r1] - rowptr[r0]) * (val ? 40 : 24) + 16);
+            char *p = b.data();
+            for (int32_t r = r0; r < r1; r++)
+                for (int32_t q = rowptr[r]; q < rowptr[r + 1]; q++) {
+                    p = put_uint(p, (uint32_t)r + 1u); *p++ = ' ';
+                    p = put_uint(p, (uint32_t)colind[q] + 1u);
+                    if (val) { *p++ = ' '; p += snprintf(p, 17, "%.9g", (double)val[q]); }
+                    *p++ = '\n';
+                }
+            b.resize((size_t)(p - b.data()));
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nthreads; t++) pool.emplace_back(work, t);
+        work(0);
+        for (auto &th : pool) th.join();
+        for (unsigned t = 0; t < nthreads && ok; t++)
+            if (!out[t].empty()) ok = fwrite(out[t].data(), 1, out[t].size(), f) == out[t].size();
+        row = cut[nthreads];
+    }
+    ok = (fclose(f) == 0) && ok;
+    return ok ? GESPMM_OK : GESPMM_ERR_IO;
+}

@@ -194,6 +194,14 @@ void gespmm_free_host(void *p);
  *                                        *cache_hit (nullable) tells which happened.
  * Arrays are malloc'ed by the library; release them with gespmm_free_host.
  */
+/*
+ * Host CSR -> MatrixMarket coordinate file, `general` symmetry, 1-based, one entry per line in CSR order; field
+ * `pattern` when val is NULL, `real` (%.9g: fp32 round-trips) otherwise.  gespmm_read_mtx of the result gives the
+ * arrays back.  (The reference's data/conv.c rewrites .mtx files entry by entry with fprintf.)
+ */
+int gespmm_write_mtx(const char *path, int32_t nrows, int32_t ncols, int64_t nnz,
+                     const int32_t *rowptr, const int32_t *colind, const float *val);
+
 int gespmm_write_csr(const char *path, int32_t nrows, int32_t ncols, int64_t nnz,
                      const int32_t *rowptr, const int32_t *colind, const float *val);
 int gespmm_read_csr(const char *path, int32_t *nrows, int32_t *ncols, int64_t *nnz,

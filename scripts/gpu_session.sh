@@ -1,7 +1,7 @@
 #!/bin/bash
 # One bounded GPU session (run through gpurun from the repo root): every step under its own timeout, most
 # important first, everything into gpurun_out/.  Usage: bash scripts/gpu_session.sh [steps...]
-#   steps: subwarp sweep ksweep suite seq auto64 bench smoke sanitize launches ncu128 ncu   (default: all, in that order)
+#   steps: subwarp sweep ksweep cli suite seq auto64 bench smoke sanitize launches ncu128 ncu   (default: all, in that order)
 cd "$(dirname "$0")/.." || exit 1
 O=gpurun_out
 mkdir -p $O
@@ -19,6 +19,8 @@ for step in $STEPS; do
       timeout 600 python scripts/sweep_narrow.py --workloads products --Ks 32,64,128,256,512 --variants -1 --tasks 0 --valued 1 --ref > $O/ksweep.txt 2> $O/ksweep.err
       timeout 600 python scripts/sweep_narrow.py --workloads reddit,citpatents,rmat --rmat-scale 1.0 --Ks 128,256 --variants -1 --tasks 0 --valued 1 --ref >> $O/ksweep.txt 2>> $O/ksweep.err
       note "ksweep rc=$?" ;;
+    cli)      # BASELINE.json configs[1] through the CLI: cit-Patents shape as a .mtx, reference kernel as the baseline cell
+      timeout 600 python scripts/cli_synthetic.py --workload citpatents --validate > $O/cli_citpatents.txt 2> $O/cli_citpatents.err; note "cli rc=$?" ;;
     suite)    # the whole GPU suite with default settings
       timeout 900 python -m pytest tests -q -m gpu > $O/t_default.log 2>&1; note "suite rc=$?" ;;
     seq)      # the SpMM suite with the sequential ring walker forced for every K

@@ -243,6 +243,43 @@ def test_binary_csr_image_and_cached_reader(pkg, tmp_path, golden_csr):
         capi.read_mtx_cached(str(tmp_path / "nope.mtx"))
 
 
+def test_mtx_writer_roundtrip(pkg, tmp_path, golden_csr):
+    """gespmm_write_mtx -> gespmm_read_mtx gives the CSR back (pattern and real, empty rows, empty matrix, a matrix large
+    enough for the multi-threaded path), and the file is what the oracle's reader restatement parses too."""
+    from gespmm_b200 import capi, graphs
+    import __graft_entry__ as entry
+    oracle = entry.load_oracle()
+    rng = np.random.default_rng(3)
+    rowptr, colind, shape = golden_csr("citeseer")
+    val = rng.standard_normal(len(colind)).astype(np.float32)
+    val[:4] = [0.0, -0.0, 1e-30, 3.4e38]
+    path = str(tmp_path / "w.mtx")
+    for v in (None, val):
+        capi.write_mtx(path, shape[0], shape[1], rowptr, colind, v)
+        nr, nc, rp, ci, vv = capi.read_mtx(path)
+        assert (nr, nc) == shape and np.array_equal(rp, rowptr) and np.array_equal(ci, colind)
+        assert np.array_equal(vv, np.ones(len(colind), np.float32) if v is None else v)
+        onr, onc, orow, ocol, oval = oracle.read_mtx(path)
+        assert np.array_equal(ocol, colind) and np.array_equal(orow, np.repeat(np.arange(shape[0]), np.diff(rowptr)))
+    assert open(path).readline().split()[:5] == ["%%MatrixMarket", "matrix", "coordinate", "real", "general"]
+    capi.write_mtx(path, 4, 9, np.zeros(5, np.int32), np.zeros(0, np.int32))
+    nr, nc, rp, ci, vv = capi.read_mtx(path)
+    assert (nr, nc, rp.tolist(), len(ci)) == (4, 9, [0] * 5, 0)
+    with pytest.raises(capi.GespmmError):   # rowptr[nrows] must equal nnz
+        capi.write_mtx(path, 2, 2, np.array([0, 1, 3], np.int32), np.array([0, 1], np.int32))
+    # > 2^20 entries: slices formatted by several threads, one row much longer than a slice's share
+    M = 50_000
+    deg = rng.integers(0, 40, M); deg[777] = 400_000
+    rp = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    ci = rng.integers(0, 60_000, rp[-1]).astype(np.int32)
+    graphs.write_mtx(path, rp, ci, N=60_000)   # goes through the library writer
+    nr, nc, rp2, ci2, vv = capi.read_mtx(path)
+    srt = np.concatenate([np.sort(ci[rp[r]:rp[r + 1]], kind="stable") for r in (0, 1, 777, M - 1)])
+    assert (nr, nc) == (M, 60_000) and np.array_equal(rp2, rp)
+    assert np.array_equal(np.concatenate([ci2[rp[r]:rp[r + 1]] for r in (0, 1, 777, M - 1)]), srt)   # the reader sorts columns inside a row
+    assert np.array_equal(np.sort(ci2), np.sort(ci))
+
+
 def test_operator_module_surface(pkg):
     from gespmm_b200 import op
     assert sorted(n for n in dir(op.spmm) if not n.startswith("_")) == ["csr2csc", "csr_spmm", "csr_spmm_no_edge_value"]
