@@ -24,6 +24,9 @@
  *                                  (util/util.hpp:286-333, spmm_test.cu:557-581)
  *   gespmm_read_mtx_cached,        no reference counterpart: the parsed CSR kept as a binary image next
  *   gespmm_write_csr / _read_csr   to the .mtx (the reference re-parses on every run, run_test.sh:5-10)
+ *   gespmm_write_mtx               the .mtx rewriting loop of data/conv.c:149-158 (fprintf per entry)
+ *   gespmm_row_sum_is_sequential   no reference counterpart (every reference kernel sums sequentially,
+ *                                  spmm_kernel.cu:56-59, 165-168): tells which rows this library does
  *   gespmm_csr_spmm_f32_host       the CLI's cudaMalloc / cudaMemcpy block around the launch
  *                                  (spmm_test.cu:609-640)
  *   gespmm_csr_spmm_f32_bparts,    no reference counterpart (the reference is single-GPU): B left
