@@ -44,3 +44,31 @@ def test_own_arm_needs_a_gpu():
         return
     res = _run("--steps", "3")
     assert res.returncode != 0 and "no CPU path" in (res.stderr + res.stdout)
+
+
+def test_committed_bench_line_carries_the_whole_contract():
+    """profiles/r01_bench_citpatents_n1.json is the own arm's line as printed on a B200 by the final kernels of round 1:
+    every key of the bench contract is there and the derived figures are consistent with each other."""
+    with open(os.path.join(ROOT, "profiles", "r01_bench_citpatents_n1.json")) as f:
+        d = json.loads(f.read())
+    assert BASE_KEYS <= set(d) and "impl" not in d
+    assert d["metric"] == "spmm_gflops" and d["unit"] == "GFLOP/s" and d["dtype"] == "f32" and d["data"] == "synthetic"
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] >= d["steps"]
+    cfg = d["config"]
+    assert "cit-Patents" in cfg["workload"] and cfg["K"] == 128 and cfg["nnz"] == 16_518_948 and "larger than L2" in cfg["l2"]
+    flops = 2.0 * cfg["nnz"] * cfg["K"]
+    assert abs(d["value"] - flops / (d["ms_per_step"] * 1e-3) / 1e9) < 1e-6 * d["value"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert abs(r["achieved"] - r["bytes_min"] / (d["ms_per_step"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    assert r["traffic"] is None or r["traffic"] > r["bytes_min"]   # ncu DRAM bytes per launch vs algorithmic bytes
+    e = d["e2e"]
+    assert e["unit"] == "GFLOP/s" and 0 < e["value"] < d["value"]
+    assert e["h2d_bytes_per_step"] >= 4 * cfg["N"] * cfg["K"] and e["d2h_bytes_per_step"] == 4 * cfg["M"] * cfg["K"]
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])
+    assert d["vs_baseline"] == d["value"] / 140.4
+    ref = d["reference_kernel_same_gpu"]
+    assert ref["bitwise_equal_to_ours"] is True and ref["ms"] > d["ms_per_step"]
