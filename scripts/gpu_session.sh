@@ -1,7 +1,7 @@
 #!/bin/bash
 # One bounded GPU session (run through gpurun from the repo root): every step under its own timeout, most
 # important first, everything into gpurun_out/.  Usage: bash scripts/gpu_session.sh [steps...]
-#   steps: subwarp sweep ksweep cli suite seq auto64 bench smoke sanitize launches ncu128 ncu   (default: all, in that order)
+#   steps: subwarp sweep ksweep cli suite seq seqsuite oddk rows auto64 bench smoke sanitize launches ncu128 ncu   (default: all, in that order)
 cd "$(dirname "$0")/.." || exit 1
 O=gpurun_out
 mkdir -p $O
@@ -25,6 +25,13 @@ for step in $STEPS; do
       timeout 900 python -m pytest tests -q -m gpu > $O/t_default.log 2>&1; note "suite rc=$?" ;;
     seq)      # the SpMM suite with the sequential ring walker forced for every K
       GESPMM_VARIANT=0 timeout 600 python -m pytest tests/test_spmm_gpu.py -q -m gpu > $O/t_seq.log 2>&1; note "seq rc=$?" ;;
+    seqsuite) # the SpMM suite with GESPMM_SEQUENTIAL=1 (row-parallel walker for K <= 64, ring walker above)
+      GESPMM_SEQUENTIAL=1 timeout 600 python -m pytest tests/test_spmm_gpu.py -q -m gpu > $O/t_sequential.log 2>&1; note "seqsuite rc=$?" ;;
+    oddk)     # class-count widths (K % 4 != 0: the scalar walker) next to the reference's kernels for K < 64
+      timeout 600 python scripts/sweep_narrow.py --workloads products,citpatents --Ks 3,7,41,47 --variants -1 --tasks 0 --valued 1,0 --ref > $O/sweep_oddk.txt 2> $O/sweep_oddk.err
+      note "oddk rc=$?" ;;
+    rows)     # sub-warp (2) vs row-parallel (4) narrow walkers on every shape
+      timeout 600 python scripts/sweep_narrow.py --variants 2,4 --tasks 0 > $O/sweep_v24.txt 2> $O/sweep_v24.err; note "rows rc=$?" ;;
     auto64)   # the SpMM suite with the sub-warp walker chosen automatically for K <= 64
       GESPMM_SUBWARP_MAX_K=64 timeout 600 python -m pytest tests/test_spmm_gpu.py -q -m gpu > $O/t_auto64.log 2>&1; note "auto64 rc=$?" ;;
     bench)

@@ -69,9 +69,12 @@ def main():
             if args.ref and M * K < 2**31:
                 L = entry.load_oracle().ref_cli_kernels()
                 Cr = torch.empty(M, K, device=dev)
-                rms = L.ref_spmm_time_ms(2, 8, M, K, rowptr.data_ptr(), colind.data_ptr(), val.data_ptr(), B.data_ptr(), Cr.data_ptr(), 2, args.iters)
+                # the kernel the reference itself would pick: the extension's K thresholds (spmm_kernel.cu:437-456) below 64,
+                # the CLI's timed configuration (spmm_test.cu:724,756) from 64 on
+                method, tile_row = (0, max(1, 128 // K)) if K < 32 else ((1, 4) if K < 64 else (2, 8))
+                rms = L.ref_spmm_time_ms(method, tile_row, M, K, rowptr.data_ptr(), colind.data_ptr(), val.data_ptr(), B.data_ptr(), Cr.data_ptr(), 2, args.iters)
                 rel = float((Cr - first).abs().max() / first.abs().max().clamp_min(1e-30))
-                print(json.dumps({"workload": wl, "M": M, "nnz": nnz, "K": K, "reference_kernel": "spmm_test2<float> tile_row 8", "ms": round(rms, 4),
+                print(json.dumps({"workload": wl, "M": M, "nnz": nnz, "K": K, "reference_kernel": "spmm_test%d<float> tile_row %d" % (method, tile_row), "ms": round(rms, 4),
                                   "gflops": round(flops / rms / 1e6, 1), "max_rel_diff_vs_ring": rel}), flush=True)
                 del Cr
             del B, first
