@@ -1,7 +1,7 @@
 #!/bin/bash
 # One bounded GPU session (run through gpurun from the repo root): every step under its own timeout, most
 # important first, everything into gpurun_out/.  Usage: bash scripts/gpu_session.sh [steps...]
-#   steps: subwarp sweep ksweep cli suite seq seqsuite oddk rows auto64 bench smoke sanitize launches ncu128 ncu   (default: all, in that order)
+#   steps: subwarp sweep ksweep cli opreddit suite seq seqsuite oddk rows auto64 bench smoke sanitize launches ncu128 ncu   (default: all, in that order)
 cd "$(dirname "$0")/.." || exit 1
 O=gpurun_out
 mkdir -p $O
@@ -21,6 +21,8 @@ for step in $STEPS; do
       note "ksweep rc=$?" ;;
     cli)      # BASELINE.json configs[1] through the CLI: cit-Patents shape as a .mtx, reference kernel as the baseline cell
       timeout 600 python scripts/cli_synthetic.py --workload citpatents --validate > $O/cli_citpatents.txt 2> $O/cli_citpatents.err; note "cli rc=$?" ;;
+    opreddit) # BASELINE.json configs[2]: Reddit shape, K = 256, SPMMFunction forward + backward next to the reference extension
+      timeout 600 python scripts/op_reddit.py > $O/op_reddit.json 2> $O/op_reddit.err; note "opreddit rc=$?" ;;
     suite)    # the whole GPU suite with default settings
       timeout 900 python -m pytest tests -q -m gpu > $O/t_default.log 2>&1; note "suite rc=$?" ;;
     seq)      # the SpMM suite with the sequential ring walker forced for every K
