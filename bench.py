@@ -44,6 +44,7 @@ import __graft_entry__ as entry  # noqa: E402
 WORKLOADS = {
     # name: (description, generator kwargs)
     "citpatents": "cit-Patents shape-alike (N=3774768, nnz=16518948), synthetic citation graph seed 1",
+    "citpatents_uniform": "cit-Patents shape-alike, uniformly random columns (N=3774768, nnz=16518948, local_fraction=0), seed 1",
     "rmat": "R-MAT(0.57,0.19,0.19,0.05) N=10000000 nnz=200000000 seed 4",
     "reddit": "Reddit shape-alike (N=232965, nnz=114615892) symmetric seed 2",
     "products": "ogbn-products shape-alike (N=2449029, nnz=123718280) symmetric seed 3",
@@ -56,6 +57,9 @@ def make_graph(name, scale, device):
     if name == "citpatents":
         N, nnz = graphs.SHAPES["cit-Patents"]
         return graphs.citation_like(N=max(2, int(N * scale)), nnz=max(2, int(nnz * scale)), seed=1, device=device)
+    if name == "citpatents_uniform":
+        N, nnz = graphs.SHAPES["cit-Patents"]
+        return graphs.citation_like(N=max(2, int(N * scale)), nnz=max(2, int(nnz * scale)), seed=1, device=device, local_fraction=0.0)
     if name == "rmat":
         N, nnz = graphs.SHAPES["rmat-10m"]
         return graphs.rmat(N=max(2, int(N * scale)), nnz=max(2, int(nnz * scale)), seed=4, device=device)

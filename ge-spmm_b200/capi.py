@@ -18,12 +18,24 @@ LONG_ROW = 4096
 
 # every symbol include/gespmm.h declares
 SYMBOLS = (
-    "gespmm_version", "gespmm_error_string", "gespmm_csr_spmm_f32", "gespmm_csr_spmm_f32_host", "gespmm_csr_spmm_f32_bparts", "gespmm_csr_spmm_max_f32", "gespmm_row_sum_is_sequential", "gespmm_enable_peer_access", "gespmm_ipc_open", "gespmm_ipc_close", "gespmm_ipc_alloc", "gespmm_ipc_free",
+    "gespmm_version", "gespmm_error_string", "gespmm_csr_spmm_f32", "gespmm_csr_spmm_f32_ex", "gespmm_opts_init", "gespmm_max_row_nnz",
+    "gespmm_reload_env", "gespmm_row_sum_is_sequential_ex", "gespmm_csr_spmm_f32_host", "gespmm_csr_spmm_f32_bparts", "gespmm_csr_spmm_max_f32", "gespmm_row_sum_is_sequential", "gespmm_enable_peer_access", "gespmm_ipc_open", "gespmm_ipc_close", "gespmm_ipc_alloc", "gespmm_ipc_free",
     "gespmm_csr2csc_workspace_bytes", "gespmm_csr2csc_f32", "gespmm_read_mtx", "gespmm_free_host",
     "gespmm_write_csr", "gespmm_read_csr", "gespmm_read_mtx_cached", "gespmm_write_mtx",
 )
 
 _lib = None
+
+FLAG_SEQUENTIAL, FLAG_NO_OVERLAP = 0x1, 0x2
+WALKER_AUTO, WALKER_RING, WALKER_REGISTER, WALKER_SUBWARP, WALKER_ROWS = 0, 1, 2, 3, 4
+
+
+class Opts(ctypes.Structure):
+    """gespmm_opts (include/gespmm.h); make one with opts(...)."""
+    _fields_ = [("struct_size", ctypes.c_uint32), ("flags", ctypes.c_uint32), ("max_row_nnz", ctypes.c_int64),
+                ("row_scale", ctypes.c_void_p), ("col_scale", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+                ("walker", ctypes.c_int32), ("task_keys", ctypes.c_int32), ("long_row", ctypes.c_int32),
+                ("panel_v", ctypes.c_int32), ("l2_policy", ctypes.c_int32), ("l2_window_rows", ctypes.c_int32)]
 
 
 class GespmmError(RuntimeError):
@@ -47,6 +59,16 @@ def lib():
         L.gespmm_error_string.argtypes = [ctypes.c_int]
         L.gespmm_csr_spmm_f32.restype = ctypes.c_int
         L.gespmm_csr_spmm_f32.argtypes = [i64, i64, i64, i64, p, p, p, p, i64, p, i64, p]
+        L.gespmm_csr_spmm_f32_ex.restype = ctypes.c_int
+        L.gespmm_csr_spmm_f32_ex.argtypes = [i64, i64, i64, i64, p, p, p, p, i64, p, i64, ctypes.POINTER(Opts), p]
+        L.gespmm_opts_init.restype = None
+        L.gespmm_opts_init.argtypes = [ctypes.POINTER(Opts)]
+        L.gespmm_max_row_nnz.restype = ctypes.c_int
+        L.gespmm_max_row_nnz.argtypes = [i64, p, ctypes.POINTER(ctypes.c_int32), p]
+        L.gespmm_reload_env.restype = None
+        L.gespmm_reload_env.argtypes = []
+        L.gespmm_row_sum_is_sequential_ex.restype = ctypes.c_int
+        L.gespmm_row_sum_is_sequential_ex.argtypes = [i64, i64, ctypes.POINTER(Opts)]
         L.gespmm_csr_spmm_f32_bparts.restype = ctypes.c_int
         L.gespmm_csr_spmm_f32_bparts.argtypes = [i64, i64, i64, i64, p, p, p, ctypes.c_int, ctypes.POINTER(p),
                                                  ctypes.POINTER(i64), i64, p, i64, p]
@@ -105,6 +127,41 @@ def csr_spmm_f32(M, N, K, nnz, rowptr, colind, val, B, ldb, C, ldc, stream=None)
         raise GespmmError(rc, "gespmm_csr_spmm_f32")
 
 
+def opts(sequential=False, no_overlap=False, max_row_nnz=-1, row_scale=None, col_scale=None, bias=None, walker=0,
+         task_keys=0, long_row=0, panel_v=0, l2_policy=0, l2_window_rows=0):
+    """A gespmm_opts initialised by the library and filled in; the scale / bias arguments are device pointers (ints)."""
+    o = Opts()
+    lib().gespmm_opts_init(ctypes.byref(o))
+    o.flags = (FLAG_SEQUENTIAL if sequential else 0) | (FLAG_NO_OVERLAP if no_overlap else 0)
+    o.max_row_nnz = int(max_row_nnz)
+    o.row_scale, o.col_scale, o.bias = row_scale or None, col_scale or None, bias or None
+    o.walker, o.task_keys, o.long_row, o.panel_v = int(walker), int(task_keys), int(long_row), int(panel_v)
+    o.l2_policy, o.l2_window_rows = int(l2_policy), int(l2_window_rows)
+    return o
+
+
+def csr_spmm_f32_ex(M, N, K, nnz, rowptr, colind, val, B, ldb, C, ldc, options=None, stream=None):
+    """gespmm_csr_spmm_f32 with per-call options (an Opts from opts(), or None)."""
+    rc = lib().gespmm_csr_spmm_f32_ex(M, N, K, nnz, rowptr, colind, val or None, B, ldb, C, ldc,
+                                      None if options is None else ctypes.byref(options), stream or None)
+    if rc != OK:
+        raise GespmmError(rc, "gespmm_csr_spmm_f32_ex")
+
+
+def max_row_nnz(M, rowptr, stream=None):
+    """Longest row of a device CSR (synchronises the stream)."""
+    out = ctypes.c_int32(0)
+    rc = lib().gespmm_max_row_nnz(int(M), rowptr, ctypes.byref(out), stream or None)
+    if rc != OK:
+        raise GespmmError(rc, "gespmm_max_row_nnz")
+    return int(out.value)
+
+
+def reload_env():
+    """Re-read the GESPMM_* tuning environment (it is read once, at the first call into the library)."""
+    lib().gespmm_reload_env()
+
+
 def csr_spmm_max_f32(M, N, K, nnz, rowptr, colind, val, B, ldb, C, ldc, init=-10000.0, stream=None):
     """Max-reduce variant (dgl-custom/binary_reduce_max.cu); init = -10000 is the reference's max_init()."""
     rc = lib().gespmm_csr_spmm_max_f32(M, N, K, nnz, rowptr, colind, val or None, B, ldb, C, ldc, float(init), stream or None)
@@ -112,8 +169,10 @@ def csr_spmm_max_f32(M, N, K, nnz, rowptr, colind, val, B, ldb, C, ldc, init=-10
         raise GespmmError(rc, "gespmm_csr_spmm_max_f32")
 
 
-def row_sum_is_sequential(K, row_nnz):
+def row_sum_is_sequential(K, row_nnz, options=None):
     """True if a row of ``row_nnz`` nonzeros at width K is summed in the reference's sequential order (bit-identical)."""
+    if options is not None:
+        return bool(lib().gespmm_row_sum_is_sequential_ex(int(K), int(row_nnz), ctypes.byref(options)))
     return bool(lib().gespmm_row_sum_is_sequential(int(K), int(row_nnz)))
 
 

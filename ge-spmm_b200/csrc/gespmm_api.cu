@@ -6,7 +6,7 @@
 
 #include "gespmm.h"
 
-extern "C" int gespmm_version(void) { return 100; /* 0.1.0 */ }
+extern "C" int gespmm_version(void) { return 200; /* 0.2.0 */ }
 
 extern "C" const char *gespmm_error_string(int code)
 {
@@ -85,7 +85,9 @@ extern "C" int gespmm_csr_spmm_f32_host(int64_t M, int64_t N, int64_t K, int64_t
     if (M < 0 || N < 0 || K < 0 || nnz < 0 || ldb < K || ldc < K) return GESPMM_ERR_INVALID_ARG;
     if (M == 0 || K == 0) return GESPMM_OK;
     if (!rowptr || !C || (nnz > 0 && (!colind || !B))) return GESPMM_ERR_INVALID_ARG;
-    if (cudaSetDevice(device) != cudaSuccess) return GESPMM_ERR_CUDA;
+    int caller_device = -1;
+    if (cudaGetDevice(&caller_device) != cudaSuccess) { cudaGetLastError(); return GESPMM_ERR_CUDA; }
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return GESPMM_ERR_CUDA; }
 
     int32_t *d_rowptr = nullptr, *d_colind = nullptr;
     float *d_val = nullptr, *d_B = nullptr, *d_C = nullptr;
@@ -103,7 +105,7 @@ extern "C" int gespmm_csr_spmm_f32_host(int64_t M, int64_t N, int64_t K, int64_t
         if (nnz > 0 && cudaMemcpyAsync(d_colind, colind, (size_t)nnz * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
         if (nnz > 0 && val && cudaMemcpyAsync(d_val, val, (size_t)nnz * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
         // dense operands are packed to stride K on the device
-        if (nB > 0 && cudaMemcpy2DAsync(d_B, (size_t)K * 4, B, (size_t)ldb * 4, (size_t)K * 4, (size_t)N,
+        if (nB > 0 && B && cudaMemcpy2DAsync(d_B, (size_t)K * 4, B, (size_t)ldb * 4, (size_t)K * 4, (size_t)N,
                                         cudaMemcpyHostToDevice, st) != cudaSuccess) break;
         rc = gespmm_csr_spmm_f32(M, N, K, nnz, d_rowptr, d_colind, d_val, d_B, K, d_C, K, st);
         if (rc != GESPMM_OK) break;
@@ -116,5 +118,6 @@ extern "C" int gespmm_csr_spmm_f32_host(int64_t M, int64_t N, int64_t K, int64_t
     if (rc != GESPMM_OK) cudaGetLastError();
     cudaFree(d_rowptr); cudaFree(d_colind); cudaFree(d_val); cudaFree(d_B); cudaFree(d_C);
     if (st) cudaStreamDestroy(st);
+    cudaSetDevice(caller_device);  // the caller's current device is left as it was found
     return rc;
 }

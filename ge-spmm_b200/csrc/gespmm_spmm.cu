@@ -78,7 +78,10 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
+#include <atomic>
+#include <mutex>
 #include <type_traits>
 
 #include "gespmm.h"
@@ -118,6 +121,15 @@ template <> struct Pack<true> {
         acc.z = acc.z > b.z ? acc.z : b.z; acc.w = acc.w > b.w ? acc.w : b.w;
     }
     static __device__ __forceinline__ T scaled(float a, const T &b) { return make_float4(a * b.x, a * b.y, a * b.z, a * b.w); }
+    // separately rounded product / sum: never contracted into an FFMA (the fused GCN pro- and epilogue must give the
+    // bits of the unfused element-wise passes, pytorch-custom/op.py:142-147)
+    static __device__ __forceinline__ T mul_rn(const T &b, float s) {
+        return make_float4(__fmul_rn(b.x, s), __fmul_rn(b.y, s), __fmul_rn(b.z, s), __fmul_rn(b.w, s));
+    }
+    static __device__ __forceinline__ void add_rn(T &acc, const T &b) {
+        acc.x = __fadd_rn(acc.x, b.x); acc.y = __fadd_rn(acc.y, b.y); acc.z = __fadd_rn(acc.z, b.z); acc.w = __fadd_rn(acc.w, b.w);
+    }
+    static __device__ __forceinline__ T ldg_or_zero(const float *p, bool on) { return on ? ldg(p) : zero(); }
 };
 template <> struct Pack<false> {
     using T = float;
@@ -130,15 +142,24 @@ template <> struct Pack<false> {
     static __device__ __forceinline__ T splat(float x) { return x; }
     static __device__ __forceinline__ void mx(T &acc, const T &b) { acc = acc > b ? acc : b; }
     static __device__ __forceinline__ T scaled(float a, const T &b) { return a * b; }
+    static __device__ __forceinline__ T mul_rn(const T &b, float s) { return __fmul_rn(b, s); }
+    static __device__ __forceinline__ void add_rn(T &acc, const T &b) { acc = __fadd_rn(acc, b); }
+    static __device__ __forceinline__ T ldg_or_zero(const float *p, bool on) { return on ? ldg(p) : zero(); }
 };
 
 // The reduction over a row: sum (FFMA / FADD, start 0) or max (start `init`, the reference's -10000 or -inf).
-template <class P, bool VALUED, bool MAXR>
+// FUSE (sum only): every gathered B row is first scaled by its column's col_scale (one rounded product), and a
+// finished row is scaled by row_scale and offset by the bias on its way out (Epilogue below).
+template <class P, bool VALUED, bool MAXR, bool FUSE = false>
 struct Reduce {
     using T = typename P::T;
+    static_assert(!(FUSE && MAXR), "the fused scaling belongs to the sum");
     static __device__ __forceinline__ T start(float init) { return MAXR ? P::splat(init) : P::zero(); }
-    static __device__ __forceinline__ void step(T &acc, float a, const T &b) {
-        if (MAXR) { if (VALUED) P::mx(acc, P::scaled(a, b)); else P::mx(acc, b); }
+    static __device__ __forceinline__ void step(T &acc, float a, const T &b, float s = 1.f) {
+        if (FUSE) {
+            const T t = P::mul_rn(b, s);
+            if (VALUED) P::fma(acc, a, t); else P::add_rn(acc, t);
+        } else if (MAXR) { if (VALUED) P::mx(acc, P::scaled(a, b)); else P::mx(acc, b); }
         else { if (VALUED) P::fma(acc, a, b); else P::add(acc, b); }
     }
     static __device__ __forceinline__ void merge(T &acc, const T &other) {
@@ -193,17 +214,52 @@ struct Operands {
     float *C;
     int ldb, ldc;
     float init;  // max-reduce: accumulator start and value of empty rows
+    // fused GCN pro-/epilogue (FUSE walkers; each nullable): C[r,:] = (sum_p val[p] * (B[c_p,:] * col_scale[c_p])) * row_scale[r] + bias
+    const float *row_scale, *col_scale, *bias;
+    // L2 eviction-priority steering of the gathers (HINT walkers): priority code of "near" / "far" rows, the distance
+    // |col - row| that separates them, and the priority of the C stores (codes: 0 normal, 1 evict_first, 2 evict_last, 3 unchanged)
+    int l2_near, l2_far, l2_store, l2_window;
     PeerMap peer;
 };
+
+// The row-end transformation of the fused walkers: acc * row_scale[row] + bias, two separately rounded operations.
+template <class P, bool FUSE>
+struct Epilogue {
+    using T = typename P::T;
+    static __device__ __forceinline__ T apply(const T &acc, float rs, const T &bias, bool has_bias) {
+        if (!FUSE) return acc;
+        T r = P::mul_rn(acc, rs);
+        if (has_bias) P::add_rn(r, bias);
+        return r;
+    }
+};
+
+__device__ __forceinline__ unsigned long long l2_policy(int code)
+{
+    unsigned long long p;
+    switch (code) {
+        case 1: asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p)); break;
+        case 2: asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p)); break;
+        case 3: asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;\n" : "=l"(p)); break;
+        default: asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;\n" : "=l"(p)); break;
+    }
+    return p;
+}
+__device__ __forceinline__ void st_hint_f4(float *p, const float4 &a, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;\n" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "l"(pol) : "memory");
+}
 
 // =================================================================================================
 // Register walker: U B-row packs in flight per lane, in registers.  Any alignment, any K.
 // =================================================================================================
-template <int V, bool VALUED, bool VEC4, int U, bool MAXR = false>
+template <int V, bool VALUED, bool VEC4, int U, bool MAXR = false, bool FUSE = false>
 struct Walker {
     using P = Pack<VEC4>;
     using T = typename P::T;
-    using R = Reduce<P, VALUED, MAXR>;
+    using R = Reduce<P, VALUED, MAXR, FUSE>;
+    using E = Epilogue<P, FUSE>;
+    static constexpr bool kFuse = FUSE;
     float init_v;
     __device__ __forceinline__ T start() const { return R::start(init_v); }
     static constexpr int kStride = 32 * P::kWidth;  // floats between a lane's consecutive packs
@@ -216,6 +272,12 @@ struct Walker {
     int ldb, ldc;
     unsigned vmask;                 // bit v set: this lane's v-th pack is inside K
     int lane;
+    // FUSE (see WalkerRing)
+    const float *__restrict__ col_scale;
+    const float *__restrict__ row_scale;
+    float my_rs;
+    T bias_v[V];
+    bool has_bias;
 
     // panel = blockIdx.y: this warp owns columns [panel * kPanel, (panel + 1) * kPanel) of B and C
     static constexpr int kPanel = 32 * V * P::kWidth;
@@ -227,25 +289,38 @@ struct Walker {
             if (col0 + v * kStride < K) vmask |= 1u << v;
         colind = o.colind; val = o.val; Bl = o.B + col0; Cl = o.C + col0; ldb = o.ldb; ldc = o.ldc; lane = ln;
         init_v = o.init;
+        if constexpr (FUSE) {
+            col_scale = o.col_scale; row_scale = o.row_scale; my_rs = 1.f;
+            has_bias = o.bias != nullptr;
+#pragma unroll
+            for (int v = 0; v < V; v++) bias_v[v] = P::ldg_or_zero(o.bias + col0 + v * kStride, has_bias && (vmask & (1u << v)));
+        }
     }
     __device__ __forceinline__ void finish(T (&)[V]) const {}  // a lane's accumulators are whole sums already
+    __device__ __forceinline__ void load_rows(int rb, int nrows) {
+        if constexpr (FUSE) my_rs = (row_scale && lane < nrows) ? __ldg(row_scale + rb + lane) : 1.f;
+    }
 
-    __device__ __forceinline__ void store_row(int row, const T (&acc)[V]) const {
-        float *c = Cl + (long long)row * ldc;
+    __device__ __forceinline__ void store_row(int rb, int rel, const T (&acc)[V]) const {
+        float *c = Cl + (long long)(rb + rel) * ldc;
+        float rs = 1.f;
+        if constexpr (FUSE) rs = __shfl_sync(kFull, my_rs, rel);
 #pragma unroll
         for (int v = 0; v < V; v++)
-            if (vmask & (1u << v)) P::stcs(c + v * kStride, acc[v]);
+            if (vmask & (1u << v)) P::stcs(c + v * kStride, FUSE ? E::apply(acc[v], rs, bias_v[v], has_bias) : acc[v]);
     }
 
     template <bool FULL>
-    __device__ __forceinline__ void batch(int mcol, float mval, int j0, unsigned live, unsigned ends, T (&acc)[V],
+    __device__ __forceinline__ void batch(int mcol, float mval, float msc, int j0, unsigned live, unsigned ends, T (&acc)[V],
                                           unsigned &rows_left, int rb) const {
         T b[U][V];
         float a[U];
+        [[maybe_unused]] float sc[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int c = __shfl_sync(kFull, mcol, j0 + u);
             if (VALUED) a[u] = __shfl_sync(kFull, mval, j0 + u);
+            if (FUSE) sc[u] = __shfl_sync(kFull, msc, j0 + u);
             if (FULL || (live & (1u << u))) {
                 const float *bp = Bl + (long long)c * ldb;
 #pragma unroll
@@ -257,9 +332,9 @@ struct Walker {
         for (int u = 0; u < U; u++) {
             if (FULL || (live & (1u << u))) {
 #pragma unroll
-                for (int v = 0; v < V; v++) R::step(acc[v], VALUED ? a[u] : 1.f, b[u][v]);
+                for (int v = 0; v < V; v++) R::step(acc[v], VALUED ? a[u] : 1.f, b[u][v], FUSE ? sc[u] : 1.f);
                 if (ends & (1u << u)) {  // last nonzero of the current row
-                    store_row(rb + __ffs(rows_left) - 1, acc);
+                    store_row(rb, __ffs(rows_left) - 1, acc);
                     rows_left &= rows_left - 1;
 #pragma unroll
                     for (int v = 0; v < V; v++) acc[v] = start();
@@ -282,6 +357,8 @@ struct Walker {
         for (int p0 = s; p0 < e; p0 += 32) {
             const int mcol = ncol;
             const float mval = nval;
+            float msc = 1.f;
+            if constexpr (FUSE) msc = (col_scale && p0 + lane < e) ? __ldg(col_scale + mcol) : 1.f;
             const int pn = p0 + 32 + lane;
             if (pn < e) {
                 ncol = __ldcs(colind + pn);
@@ -294,8 +371,8 @@ struct Walker {
 #pragma unroll 1
             for (int j0 = 0; j0 < n; j0 += U) {
                 const unsigned live = livemask >> j0, ends = endmask >> j0;
-                if ((live & ((1u << U) - 1u)) == ((1u << U) - 1u)) batch<true>(mcol, mval, j0, live, ends, acc, rows_left, rb);
-                else batch<false>(mcol, mval, j0, live, ends, acc, rows_left, rb);
+                if ((live & ((1u << U) - 1u)) == ((1u << U) - 1u)) batch<true>(mcol, mval, msc, j0, live, ends, acc, rows_left, rb);
+                else batch<false>(mcol, mval, msc, j0, live, ends, acc, rows_left, rb);
             }
         }
     }
@@ -312,6 +389,10 @@ __device__ __forceinline__ void cp_async16(unsigned saddr, const void *g)
     if (CP == 1) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(g) : "memory");
     else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(g) : "memory");
 }
+__device__ __forceinline__ void cp_async16_hint(unsigned saddr, const void *g, unsigned long long pol)
+{
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(g), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
@@ -325,9 +406,16 @@ __device__ __forceinline__ float4 lds128(unsigned saddr)
 // G rows per stage, NS stages (power of two, divides S32 = 32/G).  Stage j of a 32-nonzero chunk
 // lives in ring slot j % NS; the copies for stage j + NS - 1 are issued right before stage j is
 // consumed.  MASKED: some lanes' packs lie beyond K (K is not a multiple of 128*V).
-template <int V, bool VALUED, int G, int NS, int CP, bool MASKED, bool PEER = false, bool MAXR = false>
+// FUSE: per-column scale on the gathered rows, per-row scale + bias on the stored rows (Operands).
+// HINT: every gather carries an L2 eviction priority chosen by the lane that loaded the column from the distance
+//       between the column and the rows being summed (bit 31 of the token = "far"); C stores carry one too.
+template <int V, bool VALUED, int G, int NS, int CP, bool MASKED, bool PEER = false, bool MAXR = false, bool FUSE = false,
+          bool HINT = false>
 struct WalkerRing {
-    using R = Reduce<Pack<true>, VALUED, MAXR>;
+    using R = Reduce<Pack<true>, VALUED, MAXR, FUSE>;
+    using E = Epilogue<Pack<true>, FUSE>;
+    static constexpr bool kFuse = FUSE;
+    static_assert(!(HINT && PEER), "the L2 hints are for local B");
     float init_v;
     __device__ __forceinline__ float4 start() const { return R::start(init_v); }
     // what a lane keeps per prefetched nonzero: its column (B is one array) or the byte address of its
@@ -354,6 +442,15 @@ struct WalkerRing {
     unsigned ring;              // shared-space address of this lane's 16 bytes in (slot 0, row 0, pack 0)
     const PeerMap *peer;        // PEER: the row blocks of B (in the kernel's parameter space)
     unsigned lane_off;          // PEER: byte offset of this lane's first owned column inside a B row
+    // FUSE
+    const float *__restrict__ col_scale;
+    const float *__restrict__ row_scale;
+    float my_rs;                // row_scale of row (rb + lane) of the current 32-row batch
+    T bias_v[V];
+    bool has_bias;
+    // HINT
+    unsigned long long pol_near, pol_far, pol_store;
+    int window, cur_row;
 
     static constexpr int kPanel = 128 * V;
     __device__ __forceinline__ void init(const Operands &o, int panel, int K, int ln, unsigned ring_base) {
@@ -367,8 +464,23 @@ struct WalkerRing {
         ring = ring_base + ln * 16;
         peer = &o.peer; lane_off = (unsigned)col0 * 4u;
         init_v = o.init;
+        if constexpr (FUSE) {
+            col_scale = o.col_scale; row_scale = o.row_scale; my_rs = 1.f;
+            has_bias = o.bias != nullptr;
+#pragma unroll
+            for (int v = 0; v < V; v++) bias_v[v] = P::ldg_or_zero(o.bias + col0 + v * kStride, has_bias && (vmask & (1u << v)));
+        }
+        if constexpr (HINT) {
+            pol_near = l2_policy(o.l2_near); pol_far = l2_policy(o.l2_far); pol_store = l2_policy(o.l2_store);
+            window = o.l2_window; cur_row = 0;
+        }
     }
     __device__ __forceinline__ void finish(T (&)[V]) const {}
+
+    // FUSE: the row scales of the 32-row batch starting at rb (lane i: row rb + i), fetched next to its rowptr
+    __device__ __forceinline__ void load_rows(int rb, int nrows) {
+        if constexpr (FUSE) my_rs = (row_scale && lane < nrows) ? __ldg(row_scale + rb + lane) : 1.f;
+    }
 
     __device__ __forceinline__ Tok load_tok(int p) const {
         const int c = __ldcs(colind + p);
@@ -378,18 +490,34 @@ struct WalkerRing {
             for (int i = 1; i < kMaxParts; i++) q += (i < peer->parts && c >= peer->lo[i]) ? 1 : 0;
             return (unsigned long long)reinterpret_cast<uintptr_t>(peer->base[q]) +
                    (unsigned long long)(unsigned)(c - peer->lo[q]) * ldb_bytes;
+        } else if constexpr (HINT) {
+            const int d = c - cur_row;
+            return ((d < 0 ? -d : d) > window) ? (c | (int)0x80000000) : c;
         } else {
             return c;
         }
     }
+    // FUSE: the scale of the column a token names (1 when there is no col_scale)
+    __device__ __forceinline__ float load_scale(Tok t, bool on) const {
+        if constexpr (FUSE && !PEER) return (on && col_scale) ? __ldg(col_scale + t) : 1.f;
+        else return 1.f;
+    }
 
     __device__ __forceinline__ bool pack_on(int v) const { return !MASKED || (vmask & (1u << v)); }
 
-    __device__ __forceinline__ void store_row(int row, const T (&acc)[V]) const {
-        float *c = Cl + (long long)row * ldc;
+    // row (rb + rel) of the current batch leaves: the fused walkers scale it and add the bias on the way out
+    __device__ __forceinline__ void store_row(int rb, int rel, const T (&acc)[V]) const {
+        float *c = Cl + (long long)(rb + rel) * ldc;
+        float rs = 1.f;
+        if constexpr (FUSE) rs = __shfl_sync(kFull, my_rs, rel);
 #pragma unroll
-        for (int v = 0; v < V; v++)
-            if (pack_on(v)) P::stcs(c + v * kStride, acc[v]);
+        for (int v = 0; v < V; v++) {
+            if (pack_on(v)) {
+                const T out = FUSE ? E::apply(acc[v], rs, bias_v[v], has_bias) : acc[v];
+                if constexpr (HINT) st_hint_f4(c + v * kStride, out, pol_store);
+                else P::stcs(c + v * kStride, out);
+            }
+        }
     }
 
     // copies for the G nonzeros at chunk positions [pos0, pos0 + G) of a chunk holding n nonzeros,
@@ -401,18 +529,26 @@ struct WalkerRing {
 #pragma unroll
         for (int i0 = 0; i0 < G; i0 += UB) {
             const char *bp[UB];
+            [[maybe_unused]] unsigned long long pol[UB];
 #pragma unroll
             for (int i = 0; i < UB; i++) {
                 const Tok t = __shfl_sync(kFull, cols, pos0 + i0 + i);
                 if constexpr (PEER) bp[i] = reinterpret_cast<const char *>((uintptr_t)(t + lane_off));
-                else bp[i] = Bl + (unsigned long long)(unsigned)t * ldb_bytes;
+                else if constexpr (HINT) {
+                    bp[i] = Bl + (unsigned long long)((unsigned)t & 0x7fffffffu) * ldb_bytes;
+                    pol[i] = t < 0 ? pol_far : pol_near;
+                } else bp[i] = Bl + (unsigned long long)(unsigned)t * ldb_bytes;
             }
 #pragma unroll
             for (int i = 0; i < UB; i++) {
                 if (FULL || pos0 + i0 + i < n) {
 #pragma unroll
-                    for (int v = 0; v < V; v++)
-                        if (pack_on(v)) cp_async16<CP>(ring + slot + ((i0 + i) * V + v) * 512, bp[i] + v * 512);
+                    for (int v = 0; v < V; v++) {
+                        if (pack_on(v)) {
+                            if constexpr (HINT) cp_async16_hint(ring + slot + ((i0 + i) * V + v) * 512, bp[i] + v * 512, pol[i]);
+                            else cp_async16<CP>(ring + slot + ((i0 + i) * V + v) * 512, bp[i] + v * 512);
+                        }
+                    }
                 }
             }
         }
@@ -424,22 +560,24 @@ struct WalkerRing {
     }
 
     __device__ __forceinline__ void flush(T (&acc)[V], unsigned &rows_left, int rb) const {
-        store_row(rb + __ffs(rows_left) - 1, acc);
+        store_row(rb, __ffs(rows_left) - 1, acc);
         rows_left &= rows_left - 1;
 #pragma unroll
         for (int v = 0; v < V; v++) acc[v] = start();
     }
 
     template <bool FULL>
-    __device__ __forceinline__ void consume_impl(float vals, int pos0, int n, unsigned endmask, T (&acc)[V],
+    __device__ __forceinline__ void consume_impl(float vals, float scales, int pos0, int n, unsigned endmask, T (&acc)[V],
                                                  unsigned &rows_left, int rb, unsigned slot) const {
 #pragma unroll
         for (int i0 = 0; i0 < G; i0 += UB) {
             T b[UB][V];
             float a[UB];
+            [[maybe_unused]] float sc[UB];
 #pragma unroll
             for (int i = 0; i < UB; i++) {
                 if (VALUED) a[i] = __shfl_sync(kFull, vals, pos0 + i0 + i);
+                if (FUSE) sc[i] = __shfl_sync(kFull, scales, pos0 + i0 + i);
                 if (FULL || pos0 + i0 + i < n) {
 #pragma unroll
                     for (int v = 0; v < V; v++)
@@ -451,34 +589,37 @@ struct WalkerRing {
 #pragma unroll
                 for (int i = 0; i < UB; i++) {
 #pragma unroll
-                    for (int v = 0; v < V; v++) R::step(acc[v], VALUED ? a[i] : 1.f, b[i][v]);
+                    for (int v = 0; v < V; v++) R::step(acc[v], VALUED ? a[i] : 1.f, b[i][v], FUSE ? sc[i] : 1.f);
                 }
             } else {
 #pragma unroll
                 for (int i = 0; i < UB; i++) {
                     if (FULL || pos0 + i0 + i < n) {
 #pragma unroll
-                        for (int v = 0; v < V; v++) R::step(acc[v], VALUED ? a[i] : 1.f, b[i][v]);
+                        for (int v = 0; v < V; v++) R::step(acc[v], VALUED ? a[i] : 1.f, b[i][v], FUSE ? sc[i] : 1.f);
                         if (ends & (1u << i)) flush(acc, rows_left, rb);
                     }
                 }
             }
         }
     }
-    __device__ __forceinline__ void consume(float vals, int pos0, int n, unsigned endmask, T (&acc)[V], unsigned &rows_left,
-                                            int rb, unsigned slot) const {
-        if (pos0 + G <= n) consume_impl<true>(vals, pos0, n, endmask, acc, rows_left, rb, slot);
-        else consume_impl<false>(vals, pos0, n, endmask, acc, rows_left, rb, slot);
+    __device__ __forceinline__ void consume(float vals, float scales, int pos0, int n, unsigned endmask, T (&acc)[V],
+                                            unsigned &rows_left, int rb, unsigned slot) const {
+        if (pos0 + G <= n) consume_impl<true>(vals, scales, pos0, n, endmask, acc, rows_left, rb, slot);
+        else consume_impl<false>(vals, scales, pos0, n, endmask, acc, rows_left, rb, slot);
     }
 
-    __device__ __forceinline__ void stream(int s, int e, T (&acc)[V], int my_end, unsigned rows, int rb) const {
+    __device__ __forceinline__ void stream(int s, int e, T (&acc)[V], int my_end, unsigned rows, int rb) {
+        if constexpr (HINT) cur_row = rb;
         Tok ccol = 0, ncol = 0, fcol = 0;
         float cval = 1.f, nval = 1.f;
+        [[maybe_unused]] float csc = 1.f, nsc = 1.f;
         if (s + lane < e) {
             ccol = load_tok(s + lane);
             if (VALUED) cval = __ldcs(val + s + lane);
         }
         if (s + 32 + lane < e) ncol = load_tok(s + 32 + lane);
+        if constexpr (FUSE) csc = load_scale(ccol, s + lane < e);
         const bool my_row = (rows >> lane) & 1u;
         unsigned rows_left = rows;
 #pragma unroll
@@ -487,6 +628,7 @@ struct WalkerRing {
         for (int p0 = s; p0 < e; p0 += 32) {
             if (p0 + 64 + lane < e) fcol = load_tok(p0 + 64 + lane);
             if (VALUED && p0 + 32 + lane < e) nval = __ldcs(val + p0 + 32 + lane);
+            if constexpr (FUSE) nsc = load_scale(ncol, p0 + 32 + lane < e);  // ncol arrived one iteration ago
             const unsigned rel = (unsigned)(my_end - 1 - p0);
             const unsigned endmask = __reduce_or_sync(kFull, (my_row && rel < 32u) ? (1u << rel) : 0u);
             const int n = min(32, e - p0);
@@ -498,9 +640,10 @@ struct WalkerRing {
                 const bool nxt = jj >= S32;
                 issue(nxt ? ncol : ccol, (jj & (S32 - 1)) * G, nxt ? n_next : n, (jj & (NS - 1)) * kStageBytes);
                 cp_async_wait<L>();
-                consume(cval, j * G, n, endmask, acc, rows_left, rb, (j & (NS - 1)) * kStageBytes);
+                consume(cval, csc, j * G, n, endmask, acc, rows_left, rb, (j & (NS - 1)) * kStageBytes);
             }
             ccol = ncol; ncol = fcol; cval = nval;
+            if constexpr (FUSE) csc = nsc;
         }
         cp_async_wait<0>();
     }
@@ -518,11 +661,13 @@ struct WalkerRing {
 // (group g with g ^ NG/2, then ^ NG/4, ...) and group 0 stores the row.  Deterministic, but NOT the
 // reference's strictly sequential order: results differ from it by fp32 re-association (max-reduce:
 // still bit-identical).  gespmm_row_sum_is_sequential() tells callers which rows that applies to.
-template <int NG, bool VALUED, bool MAXR = false>
+template <int NG, bool VALUED, bool MAXR = false, bool FUSE = false>
 struct WalkerSub {
     using P = Pack<true>;
     using T = float4;
-    using R = Reduce<P, VALUED, MAXR>;
+    using R = Reduce<P, VALUED, MAXR, FUSE>;
+    using E = Epilogue<P, FUSE>;
+    static constexpr bool kFuse = FUSE;
     static_assert(NG == 2 || NG == 4 || NG == 8, "2, 4 or 8 B rows per warp-wide copy");
     static constexpr int LPR = 32 / NG;             // lanes per B row, one float4 each
     static constexpr int Q = 32 / NG;               // quads per 32-nonzero chunk
@@ -545,6 +690,12 @@ struct WalkerSub {
     int lane, g;                  // g = lane / LPR: which nonzero of a quad this lane works on
     bool active;                  // this lane's 4 columns lie inside K
     unsigned ring;                // shared-space address of this lane's 16 bytes in (stage 0, quad 0)
+    // FUSE (see WalkerRing)
+    const float *__restrict__ col_scale;
+    const float *__restrict__ row_scale;
+    float my_rs;
+    T bias_v;
+    bool has_bias;
 
     __device__ __forceinline__ T start() const { return R::start(init_v); }
 
@@ -556,11 +707,25 @@ struct WalkerSub {
         ldb_bytes = (unsigned)o.ldb * 4u; ldc = o.ldc;
         ring = ring_base + ln * 16;
         init_v = o.init;
+        if constexpr (FUSE) {
+            col_scale = o.col_scale; row_scale = o.row_scale; my_rs = 1.f;
+            has_bias = o.bias != nullptr;
+            bias_v = P::ldg_or_zero(o.bias + col0, has_bias && active);
+        }
+    }
+    __device__ __forceinline__ void load_rows(int rb, int nrows) {
+        if constexpr (FUSE) my_rs = (row_scale && lane < nrows) ? __ldg(row_scale + rb + lane) : 1.f;
+    }
+    __device__ __forceinline__ float load_scale(int c, bool on) const {
+        if constexpr (FUSE) return (on && col_scale) ? __ldg(col_scale + c) : 1.f;
+        else return 1.f;
     }
 
     // whole-row values live in group 0 (after combine: in every group)
-    __device__ __forceinline__ void store_row(int row, const T (&acc)[1]) const {
-        if (g == 0 && active) P::stcs(Cl + (long long)row * ldc, acc[0]);
+    __device__ __forceinline__ void store_row(int rb, int rel, const T (&acc)[1]) const {
+        float rs = 1.f;
+        if constexpr (FUSE) rs = __shfl_sync(kFull, my_rs, rel);
+        if (g == 0 && active) P::stcs(Cl + (long long)(rb + rel) * ldc, FUSE ? E::apply(acc[0], rs, bias_v, has_bias) : acc[0]);
     }
 
     __device__ __forceinline__ void combine(T &t) const {
@@ -578,7 +743,10 @@ struct WalkerSub {
     __device__ __forceinline__ void flush(T &acc, unsigned &rows_left, int rb) const {
         T t = acc;
         combine(t);
-        if (g == 0 && active) P::stcs(Cl + (long long)(rb + __ffs(rows_left) - 1) * ldc, t);
+        const int rel = __ffs(rows_left) - 1;
+        float rs = 1.f;
+        if constexpr (FUSE) rs = __shfl_sync(kFull, my_rs, rel);
+        if (g == 0 && active) P::stcs(Cl + (long long)(rb + rel) * ldc, FUSE ? E::apply(t, rs, bias_v, has_bias) : t);
         rows_left &= rows_left - 1;
         acc = start();
     }
@@ -607,22 +775,24 @@ struct WalkerSub {
     }
 
     template <bool FULL>
-    __device__ __forceinline__ void consume_impl(float vals, int pos0, int n, unsigned endmask, T &acc,
+    __device__ __forceinline__ void consume_impl(float vals, float scales, int pos0, int n, unsigned endmask, T &acc,
                                                  unsigned &rows_left, int rb, unsigned slot) const {
 #pragma unroll
         for (int i0 = 0; i0 < QS; i0 += UB) {
             T b[UB];
             float a[UB];
+            float sc[UB];
 #pragma unroll
             for (int i = 0; i < UB; i++) {
                 // read back unconditionally: a slice that was not copied this time (nonzero beyond n, columns
                 // beyond K) holds stale ring bytes that are never added to anything that is stored
                 a[i] = VALUED ? __shfl_sync(kFull, vals, pos0 + (i0 + i) * NG + g) : 1.f;
+                sc[i] = FUSE ? __shfl_sync(kFull, scales, pos0 + (i0 + i) * NG + g) : 1.f;
                 b[i] = lds128(ring + slot + (i0 + i) * 512);
             }
             if (FULL && ((endmask >> (pos0 + i0 * NG)) & low_bits(UB * NG)) == 0u) {  // no row ends in these UB quads
 #pragma unroll
-                for (int i = 0; i < UB; i++) R::step(acc, a[i], b[i]);
+                for (int i = 0; i < UB; i++) R::step(acc, a[i], b[i], sc[i]);
                 continue;
             }
 #pragma unroll
@@ -630,36 +800,38 @@ struct WalkerSub {
                 const bool live = FULL || (pos0 + (i0 + i) * NG + g < n);
                 unsigned e4 = (endmask >> (pos0 + (i0 + i) * NG)) & ((1u << NG) - 1u);  // bit x: a row ends at group x's nonzero
                 if (e4 == 0u) {  // warp-uniform: no row ends inside this quad (the common case for rows >> NG)
-                    if (live) R::step(acc, a[i], b[i]);
+                    if (live) R::step(acc, a[i], b[i], sc[i]);
                 } else {
                     int lo = 0;  // groups below `lo` already added their nonzero of this quad (to an earlier row)
                     do {
                         const int hi = __ffs(e4) - 1;
-                        if (live && g >= lo && g <= hi) R::step(acc, a[i], b[i]);
+                        if (live && g >= lo && g <= hi) R::step(acc, a[i], b[i], sc[i]);
                         flush(acc, rows_left, rb);
                         lo = hi + 1;
                         e4 &= e4 - 1;
                     } while (e4);
-                    if (live && g >= lo) R::step(acc, a[i], b[i]);
+                    if (live && g >= lo) R::step(acc, a[i], b[i], sc[i]);
                 }
             }
         }
     }
-    __device__ __forceinline__ void consume(float vals, int pos0, int n, unsigned endmask, T &acc, unsigned &rows_left,
-                                            int rb, unsigned slot) const {
-        if (pos0 + SN <= n) consume_impl<true>(vals, pos0, n, endmask, acc, rows_left, rb, slot);
-        else consume_impl<false>(vals, pos0, n, endmask, acc, rows_left, rb, slot);
+    __device__ __forceinline__ void consume(float vals, float scales, int pos0, int n, unsigned endmask, T &acc,
+                                            unsigned &rows_left, int rb, unsigned slot) const {
+        if (pos0 + SN <= n) consume_impl<true>(vals, scales, pos0, n, endmask, acc, rows_left, rb, slot);
+        else consume_impl<false>(vals, scales, pos0, n, endmask, acc, rows_left, rb, slot);
     }
 
     // same contract as WalkerRing::stream; with rows == 0 the groups' partials are left in acc (see finish)
     __device__ __forceinline__ void stream(int s, int e, T (&acc)[1], int my_end, unsigned rows, int rb) const {
         int ccol = 0, ncol = 0, fcol = 0;
         float cval = 1.f, nval = 1.f;
+        [[maybe_unused]] float csc = 1.f, nsc = 1.f;
         if (s + lane < e) {
             ccol = __ldcs(colind + s + lane);
             if (VALUED) cval = __ldcs(val + s + lane);
         }
         if (s + 32 + lane < e) ncol = __ldcs(colind + s + 32 + lane);
+        if constexpr (FUSE) csc = load_scale(ccol, s + lane < e);
         const bool my_row = (rows >> lane) & 1u;
         unsigned rows_left = rows;
         unsigned slot = 0;  // stage being consumed; the other one is being filled
@@ -668,6 +840,7 @@ struct WalkerSub {
         for (int p0 = s; p0 < e; p0 += 32) {
             if (p0 + 64 + lane < e) fcol = __ldcs(colind + p0 + 64 + lane);
             if (VALUED && p0 + 32 + lane < e) nval = __ldcs(val + p0 + 32 + lane);
+            if constexpr (FUSE) nsc = load_scale(ncol, p0 + 32 + lane < e);
             const unsigned rel = (unsigned)(my_end - 1 - p0);
             const unsigned endmask = __reduce_or_sync(kFull, (my_row && rel < 32u) ? (1u << rel) : 0u);
             const int n = min(32, e - p0);
@@ -678,10 +851,11 @@ struct WalkerSub {
                 const bool nxt = j + 1 >= SPC;  // the stage to fill next opens the next chunk
                 issue(nxt ? ncol : ccol, nxt ? 0 : (j + 1) * SN, nxt ? n_next : n, slot ^ kStageBytes);
                 cp_async_wait<1>();
-                consume(cval, j * SN, n, endmask, acc[0], rows_left, rb, slot);
+                consume(cval, csc, j * SN, n, endmask, acc[0], rows_left, rb, slot);
                 slot ^= kStageBytes;
             }
             ccol = ncol; ncol = fcol; cval = nval;
+            if constexpr (FUSE) csc = nsc;
         }
         cp_async_wait<0>();
     }
@@ -701,11 +875,12 @@ struct WalkerSub {
 // run takes as many chunks as its longest group needs (measured on the generators' degree
 // distributions: 95-97 % of ideal at NG = 2, 82-92 % at NG = 4, 53-73 % at NG = 8).
 // Rows only; kernel B (long rows, re-associated anyway) pairs it with WalkerSub.
-template <int NG, bool VALUED, bool MAXR = false>
+template <int NG, bool VALUED, bool MAXR = false, bool FUSE = false>
 struct WalkerRows {
     using P = Pack<true>;
     using T = float4;
-    using R = Reduce<P, VALUED, MAXR>;
+    using R = Reduce<P, VALUED, MAXR, FUSE>;
+    using E = Epilogue<P, FUSE>;
     static_assert(NG == 2 || NG == 4 || NG == 8, "2, 4 or 8 row blocks per warp");
     static constexpr int LPR = 32 / NG;             // lanes per group = nonzeros per group per chunk
     static constexpr int QS = LPR < 8 ? LPR : 8;    // steps per ring stage
@@ -727,6 +902,12 @@ struct WalkerRows {
     int lane, g, sl;              // group and position inside the group
     bool active;                  // this lane's 4 columns lie inside K
     unsigned ring;
+    // FUSE (see WalkerRing)
+    const float *__restrict__ col_scale;
+    const float *__restrict__ row_scale;
+    float my_rs;
+    T bias_v;
+    bool has_bias;
 
     __device__ __forceinline__ T start() const { return R::start(init_v); }
 
@@ -738,11 +919,25 @@ struct WalkerRows {
         ldb_bytes = (unsigned)o.ldb * 4u; ldc = o.ldc;
         ring = ring_base + ln * 16;
         init_v = o.init;
+        if constexpr (FUSE) {
+            col_scale = o.col_scale; row_scale = o.row_scale; my_rs = 1.f;
+            has_bias = o.bias != nullptr;
+            bias_v = P::ldg_or_zero(o.bias + col0, has_bias && active);
+        }
+    }
+    __device__ __forceinline__ void load_rows(int rb, int nrows) {
+        if constexpr (FUSE) my_rs = (row_scale && lane < nrows) ? __ldg(row_scale + rb + lane) : 1.f;
+    }
+    __device__ __forceinline__ float load_scale(int c, bool on) const {
+        if constexpr (FUSE) return (on && col_scale) ? __ldg(col_scale + c) : 1.f;
+        else return 1.f;
     }
 
     // kernel A's empty rows: one group writes the row
-    __device__ __forceinline__ void store_row(int row, const T (&acc)[1]) const {
-        if (g == 0 && active) P::stcs(Cl + (long long)row * ldc, acc[0]);
+    __device__ __forceinline__ void store_row(int rb, int rel, const T (&acc)[1]) const {
+        float rs = 1.f;
+        if constexpr (FUSE) rs = __shfl_sync(kFull, my_rs, rel);
+        if (g == 0 && active) P::stcs(Cl + (long long)(rb + rel) * ldc, FUSE ? E::apply(acc[0], rs, bias_v, has_bias) : acc[0]);
     }
 
     // copies for steps [k0, k0 + QS) of a chunk in which my group still has n nonzeros; one commit group
@@ -763,28 +958,33 @@ struct WalkerRows {
     }
 
     // steps [k0, k0 + QS) of the chunk: n = my group's nonzeros left, nmin = the least over the groups
-    __device__ __forceinline__ void consume(float vals, int k0, int n, int nmin, unsigned endmask, T &acc, unsigned &left,
-                                            int rb, unsigned slot) const {
+    __device__ __forceinline__ void consume(float vals, float scales, int k0, int n, int nmin, unsigned endmask, T &acc,
+                                            unsigned &left, int rb, unsigned slot) const {
 #pragma unroll
         for (int i0 = 0; i0 < QS; i0 += UB) {
             T b[UB];
             float a[UB];
+            float sc[UB];
 #pragma unroll
             for (int i = 0; i < UB; i++) {
                 a[i] = VALUED ? __shfl_sync(kFull, vals, k0 + i0 + i, LPR) : 1.f;
+                sc[i] = FUSE ? __shfl_sync(kFull, scales, k0 + i0 + i, LPR) : 1.f;
                 b[i] = lds128(ring + slot + (i0 + i) * 512);  // stale bytes where nothing was copied: never added
             }
             const unsigned ends = endmask & ((kGroupOnes * ((1u << UB) - 1u)) << (k0 + i0));  // any group, these UB steps
             if (ends == 0u && nmin >= k0 + i0 + UB) {  // warp-uniform: every group is live and no row ends
 #pragma unroll
-                for (int i = 0; i < UB; i++) R::step(acc, a[i], b[i]);
+                for (int i = 0; i < UB; i++) R::step(acc, a[i], b[i], sc[i]);
             } else {
 #pragma unroll
                 for (int i = 0; i < UB; i++) {
                     const int k = k0 + i0 + i;
-                    if (k < n) R::step(acc, a[i], b[i]);
+                    if (k < n) R::step(acc, a[i], b[i], sc[i]);
+                    const int rel = (__ffs(left) - 1) & 31;  // my group's current row (any lane when the group is done)
+                    float rs = 1.f;
+                    if constexpr (FUSE) rs = __shfl_sync(kFull, my_rs, rel);  // every lane takes part: the groups diverge below
                     if ((endmask >> (g * LPR + k)) & 1u) {  // my group's current row ends with this nonzero
-                        if (active) P::stcs(Cl + (long long)(rb + __ffs(left) - 1) * ldc, acc);
+                        if (active) P::stcs(Cl + (long long)(rb + rel) * ldc, FUSE ? E::apply(acc, rs, bias_v, has_bias) : acc);
                         left &= left - 1;
                         acc = start();
                     }
@@ -820,17 +1020,20 @@ struct WalkerRows {
         int p = gs;
         int ccol = 0, ncol = 0, fcol = 0;
         float cval = 1.f, nval = 1.f;
+        [[maybe_unused]] float csc = 1.f, nsc = 1.f;
         if (p + sl < ge) {
             ccol = __ldcs(colind + p + sl);
             if (VALUED) cval = __ldcs(val + p + sl);
         }
         if (p + LPR + sl < ge) ncol = __ldcs(colind + p + LPR + sl);
+        if constexpr (FUSE) csc = load_scale(ccol, p + sl < ge);
         unsigned slot = 0;
         issue(ccol, 0, ge - p, 0);
 #pragma unroll 1
         for (int c0 = 0; c0 < maxlen; c0 += LPR, p += LPR) {
             if (p + 2 * LPR + sl < ge) fcol = __ldcs(colind + p + 2 * LPR + sl);
             if (VALUED && p + LPR + sl < ge) nval = __ldcs(val + p + LPR + sl);
+            if constexpr (FUSE) nsc = load_scale(ncol, p + LPR + sl < ge);
             // row ends of every group inside this chunk: one LPR-bit field per group
             const unsigned rel = (unsigned)(my_end - 1 - (row_gs + c0));
             const unsigned endmask = __reduce_or_sync(kFull, (my_row && rel < (unsigned)LPR) ? (1u << (grp * LPR + rel)) : 0u);
@@ -842,10 +1045,11 @@ struct WalkerRows {
                 const bool nxt = j + 1 >= SPC;
                 issue(nxt ? ncol : ccol, nxt ? 0 : (j + 1) * QS, nxt ? n - LPR : n, slot ^ kStageBytes);
                 cp_async_wait<1>();
-                consume(cval, j * QS, n, nmin, endmask, acc, left, rb, slot);
+                consume(cval, csc, j * QS, n, nmin, endmask, acc, left, rb, slot);
                 slot ^= kStageBytes;
             }
             ccol = ncol; ncol = fcol; cval = nval;
+            if constexpr (FUSE) csc = nsc;
         }
         cp_async_wait<0>();
         accv[0] = acc;
@@ -885,6 +1089,7 @@ spmm_flat_kernel(int M, int K, long long total_keys, int task, int long_row, con
             my_start = __ldg(rowptr + rb + lane);
             my_end = __ldg(rowptr + rb + lane + 1);
         }
+        wk.load_rows(rb, nrows);
         const int len = my_end - my_start;
         unsigned long_mask = __ballot_sync(kFull, len > long_row);  // left to kernel B
         const unsigned nonempty = __ballot_sync(kFull, len > 0) & ~long_mask;
@@ -894,7 +1099,7 @@ spmm_flat_kernel(int M, int K, long long total_keys, int task, int long_row, con
 #pragma unroll
             for (int v = 0; v < V; v++) z[v] = wk.start();
             while (em) {
-                wk.store_row(rb + __ffs(em) - 1, z);
+                wk.store_row(rb, __ffs(em) - 1, z);
                 em &= em - 1;
             }
         }
@@ -992,7 +1197,12 @@ spmm_long_kernel(int M, int K, int nnz, int long_row, const int *__restrict__ ro
 #pragma unroll
             for (int w = 1; w < kLongWarps; w++) WK::R::merge(sum, part[w][x]);
             const int c = blockIdx.y * WK::kPanel + x * W;
-            if (c < K) P::stcs(op.C + (long long)r * op.ldc + c, sum);
+            if (c < K) {
+                if constexpr (WK::kFuse)
+                    sum = Epilogue<P, true>::apply(sum, op.row_scale ? __ldg(op.row_scale + r) : 1.f,
+                                                   P::ldg_or_zero(op.bias + c, op.bias != nullptr), op.bias != nullptr);
+                P::stcs(op.C + (long long)r * op.ldc + c, sum);
+            }
         }
     }
 
@@ -1029,7 +1239,12 @@ spmm_long_kernel(int M, int K, int nnz, int long_row, const int *__restrict__ ro
                     T sum = s_cpart[x];
                     for (unsigned c2 = 1; c2 < csize; c2++) WK::R::merge(sum, cluster.map_shared_rank(s_cpart, c2)[x]);
                     const int c = blockIdx.y * WK::kPanel + x * W;
-                    if (c < K) P::stcs(op.C + (long long)r * op.ldc + c, sum);
+                    if (c < K) {
+                        if constexpr (WK::kFuse)
+                            sum = Epilogue<P, true>::apply(sum, op.row_scale ? __ldg(op.row_scale + r) : 1.f,
+                                                           P::ldg_or_zero(op.bias + c, op.bias != nullptr), op.bias != nullptr);
+                        P::stcs(op.C + (long long)r * op.ldc + c, sum);
+                    }
                 }
             }
             cluster.sync();  // partials consumed: s_part / s_cpart may be rewritten
@@ -1043,7 +1258,9 @@ spmm_long_kernel(int M, int K, int nnz, int long_row, const int *__restrict__ ro
 // =================================================================================================
 struct Args {
     int M, K, task, long_row;
-    bool overlap;  // run kernel B concurrently with kernel A (helper stream)
+    bool overlap;   // run kernel B concurrently with kernel A (helper stream)
+    bool has_long;  // some row may be longer than long_row: kernel B is needed
+    int smem_pad;   // extra dynamic shared memory per CTA of kernel A (tuning: caps the resident CTAs per SM)
     long long nnz;
     const int *rowptr;
     Operands op;
@@ -1070,32 +1287,49 @@ Side *side_for_current_device()
     if (!sd.ok) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = greatest priority: the long rows should be placed first
-        if (cudaStreamCreateWithPriority(&sd.stream, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        const bool made = cudaStreamCreateWithPriority(&sd.stream, cudaStreamNonBlocking, hi) == cudaSuccess &&
+                          cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming) == cudaSuccess &&
+                          cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming) == cudaSuccess;
+        if (!made) {  // nothing half-made is kept
+            if (sd.join) cudaEventDestroy(sd.join);
+            if (sd.fork) cudaEventDestroy(sd.fork);
+            if (sd.stream) cudaStreamDestroy(sd.stream);
+            sd = Side();
+            cudaGetLastError();
+            return nullptr;
+        }
         sd.ok = true;
     }
     return &sd;
+}
+
+// Opt a kernel into more than 48 KB of dynamic shared memory, once per (kernel, device).
+template <class KernelT>
+cudaError_t allow_smem(KernelT kern, int bytes, std::atomic<bool> (&done)[kMaxDevices])
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    if (!done[dev].load(std::memory_order_acquire)) {
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        done[dev].store(true, std::memory_order_release);
+    }
+    return cudaSuccess;
 }
 
 template <class WK, int V, bool VEC4, int MINB, class WKB = WK>
 cudaError_t launch(const Args &a)
 {
     const unsigned panels = (unsigned)((a.K + WK::kPanel - 1) / WK::kPanel);
-    const bool has_b = a.nnz > a.long_row;
+    const bool has_b = a.has_long;
     Side *sd = (has_b && a.overlap) ? side_for_current_device() : nullptr;
     if (has_b) {
         constexpr int dynB = WKB::kRingBytes * kLongWarps;
         auto kernB = spmm_long_kernel<WKB, V, VEC4>;
-        if (dynB > 0) {  // static + dynamic shared memory exceeds the 48 KB default: opt in, once per device
-            static bool done[kMaxDevices] = {};
-            int dev = 0;
-            cudaGetDevice(&dev);
-            if (dev >= 0 && dev < kMaxDevices && !done[dev]) {
-                const cudaError_t e = cudaFuncSetAttribute(kernB, cudaFuncAttributeMaxDynamicSharedMemorySize, dynB);
-                if (e != cudaSuccess) return e;
-                done[dev] = true;
-            }
+        if (dynB > 0) {  // static + dynamic shared memory exceeds the 48 KB default
+            static std::atomic<bool> done[kMaxDevices];
+            const cudaError_t e = allow_smem(kernB, dynB, done);
+            if (e != cudaSuccess) return e;
         }
         cudaStream_t sb = a.st;
         if (sd) {
@@ -1113,13 +1347,15 @@ cudaError_t launch(const Args &a)
     const long long total = a.nnz + a.M;
     const long long ntask = (total + a.task - 1) / a.task;
     dim3 grid((unsigned)ntask, panels, 1);
-    kernA<<<grid, 32, dynA, a.st>>>(a.M, a.K, total, a.task, a.long_row, a.rowptr, a.op);
+    int pad = a.smem_pad;
+    if (pad < 0 || dynA + pad > 48 * 1024) pad = 0;
+    kernA<<<grid, 32, dynA + pad, a.st>>>(a.M, a.K, total, a.task, a.long_row, a.rowptr, a.op);
     if (sd && cudaStreamWaitEvent(a.st, sd->join, 0) != cudaSuccess) return cudaGetLastError();
     return cudaGetLastError();
 }
 
-template <int V, bool VALUED, bool VEC4, int U, int MINB, bool MAXR = false>
-cudaError_t launch_reg(const Args &a) { return launch<Walker<V, VALUED, VEC4, U, MAXR>, V, VEC4, MINB>(a); }
+template <int V, bool VALUED, bool VEC4, int U, int MINB, bool MAXR = false, bool FUSE = false>
+cudaError_t launch_reg(const Args &a) { return launch<Walker<V, VALUED, VEC4, U, MAXR, FUSE>, V, VEC4, MINB>(a); }
 
 int env_int(const char *name, int dflt)
 {
@@ -1128,12 +1364,87 @@ int env_int(const char *name, int dflt)
 }
 
 constexpr int kMaxLong = 1 << 20;  // largest accepted long-row threshold: a 32-row run then spans < 2^25 nonzeros
-// GESPMM_LONG: tuning override of GESPMM_LONG_ROW, clamped to [kMinLong, kMaxLong]
-int long_row_threshold()
+constexpr int kSubwarpMaxKDefault = 64;  // measured on B200 (profiles/r01_sweep_narrow.txt): 1.1-6x the ring walker at K <= 64
+constexpr int kL2WindowDefault = 1 << 17;  // rows: 64 MB of 512-byte panel rows, about half of the L2
+
+// The GESPMM_* tuning environment, read once (gespmm_reload_env re-reads it):
+//   GESPMM_VARIANT unset / < 0 : automatic -- the sub-warp walker for K <= GESPMM_SUBWARP_MAX_K, else the ring walker
+//     0 ring walker (sequential order for every K)   1 register-staged walker (comparisons)
+//     2 sub-warp walker wherever it applies (K <= 64)   4 row-parallel narrow walker wherever it applies (sequential)
+//   GESPMM_SEQUENTIAL=1 : the fastest walker that keeps the reference's order for every K (= variant 4)
+//   GESPMM_TASK / GESPMM_LONG / GESPMM_PANEL_V / GESPMM_OVERLAP / GESPMM_SMEM_PAD : launch-shape overrides
+//   GESPMM_L2_POLICY = near + 4 far + 16 store (each 0 normal, 1 evict_first, 2 evict_last, 3 unchanged), GESPMM_L2_WINDOW rows
+struct Tuning {
+    int task, long_row, walker, panel_v, overlap, subwarp_max_k, l2_policy, l2_window, smem_pad;
+};
+int walker_of_variant(int variant)
 {
+    switch (variant) {
+        case 0: return GESPMM_WALKER_RING;
+        case 1: return GESPMM_WALKER_REGISTER;
+        case 2: return GESPMM_WALKER_SUBWARP;
+        case 4: return GESPMM_WALKER_ROWS;
+        default: return GESPMM_WALKER_AUTO;
+    }
+}
+Tuning read_env()
+{
+    Tuning t;
+    t.task = env_int("GESPMM_TASK", 0);
     const int forced = env_int("GESPMM_LONG", 0);
-    if (forced < kMinLong) return GESPMM_LONG_ROW;
-    return forced > kMaxLong ? kMaxLong : forced;
+    t.long_row = forced < kMinLong ? GESPMM_LONG_ROW : (forced > kMaxLong ? kMaxLong : forced);
+    t.walker = env_int("GESPMM_SEQUENTIAL", 0) != 0 ? GESPMM_WALKER_ROWS : walker_of_variant(env_int("GESPMM_VARIANT", -1));
+    t.panel_v = env_int("GESPMM_PANEL_V", 0);
+    t.overlap = env_int("GESPMM_OVERLAP", 1);
+    t.subwarp_max_k = env_int("GESPMM_SUBWARP_MAX_K", kSubwarpMaxKDefault);
+    t.l2_policy = env_int("GESPMM_L2_POLICY", 0);
+    t.l2_window = env_int("GESPMM_L2_WINDOW", kL2WindowDefault);
+    t.smem_pad = env_int("GESPMM_SMEM_PAD", 0);
+    return t;
+}
+Tuning g_tuning;
+std::once_flag g_tuning_once;
+const Tuning &tuning()
+{
+    std::call_once(g_tuning_once, [] { g_tuning = read_env(); });
+    return g_tuning;
+}
+
+// One call's choices: the environment's, overridden field by field by the caller's gespmm_opts.
+struct Choice {
+    int walker, task, long_row, panel_v, l2_policy, l2_window, smem_pad;
+    bool overlap;
+    long long max_row_nnz;
+    const float *row_scale, *col_scale, *bias;
+    bool fuse() const { return row_scale || col_scale || bias; }
+};
+Choice choose(const gespmm_opts *o)
+{
+    const Tuning &t = tuning();
+    Choice c;
+    c.walker = t.walker; c.task = t.task; c.long_row = t.long_row; c.panel_v = t.panel_v; c.l2_policy = t.l2_policy;
+    c.l2_window = t.l2_window; c.smem_pad = t.smem_pad; c.overlap = t.overlap != 0; c.max_row_nnz = -1;
+    c.row_scale = c.col_scale = c.bias = nullptr;
+    if (o) {
+        if (o->walker > 0) c.walker = o->walker;
+        if (o->flags & GESPMM_FLAG_SEQUENTIAL) c.walker = GESPMM_WALKER_ROWS;
+        if (o->flags & GESPMM_FLAG_NO_OVERLAP) c.overlap = false;
+        if (o->task_keys > 0) c.task = o->task_keys;
+        if (o->long_row >= kMinLong) c.long_row = o->long_row > kMaxLong ? kMaxLong : o->long_row;
+        if (o->panel_v > 0) c.panel_v = o->panel_v;
+        if (o->l2_policy > 0) c.l2_policy = o->l2_policy;
+        if (o->l2_window_rows > 0) c.l2_window = o->l2_window_rows;
+        c.max_row_nnz = o->max_row_nnz;
+        c.row_scale = o->row_scale; c.col_scale = o->col_scale; c.bias = o->bias;
+    }
+    return c;
+}
+bool use_rows(int64_t K, int walker) { return walker == GESPMM_WALKER_ROWS && K <= 64 && K % 4 == 0; }
+bool use_subwarp(int64_t K, int walker)
+{
+    if (K > 64 || K % 4 != 0) return false;
+    if (walker == GESPMM_WALKER_SUBWARP) return true;
+    return walker == GESPMM_WALKER_AUTO && K <= tuning().subwarp_max_k;
 }
 
 // Default ring shape per V: (G rows per stage, MINB CTAs per SM); two stages.
@@ -1143,100 +1454,126 @@ template <> struct Shape<2> { static constexpr int G = 4, MINB = 20; };
 template <> struct Shape<3> { static constexpr int G = 2, MINB = 24; };
 template <> struct Shape<4> { static constexpr int G = 2, MINB = 16; };
 
-template <int V, bool VALUED, bool PEER, bool MAXR>
-cudaError_t launch_default(const Args &a, bool masked)
+template <int V, bool VALUED, bool PEER, bool MAXR, bool FUSE = false, bool HINT = false>
+cudaError_t launch_ring(const Args &a, bool masked)
 {
     constexpr int G = Shape<V>::G, MINB = Shape<V>::MINB;
-    return masked ? launch<WalkerRing<V, VALUED, G, 2, 0, true, PEER, MAXR>, V, true, MINB>(a)
-                  : launch<WalkerRing<V, VALUED, G, 2, 0, false, PEER, MAXR>, V, true, MINB>(a);
+    return masked ? launch<WalkerRing<V, VALUED, G, 2, 0, true, PEER, MAXR, FUSE, HINT>, V, true, MINB>(a)
+                  : launch<WalkerRing<V, VALUED, G, 2, 0, false, PEER, MAXR, FUSE, HINT>, V, true, MINB>(a);
+}
+template <bool VALUED, bool PEER, bool MAXR>
+cudaError_t dispatch_ring(int V, const Args &a, bool masked)
+{
+    switch (V) {
+        case 1: return launch_ring<1, VALUED, PEER, MAXR>(a, masked);
+        case 2: return launch_ring<2, VALUED, PEER, MAXR>(a, masked);
+        case 3: return launch_ring<3, VALUED, PEER, MAXR>(a, masked);
+        default: return launch_ring<4, VALUED, PEER, MAXR>(a, masked);
+    }
 }
 
 // Narrow B (K <= 64, aligned operands): NG = 2 / 4 / 8 nonzeros per warp-wide copy for K <= 64 / 32 / 16.
-template <bool VALUED, bool MAXR>
+template <bool VALUED, bool MAXR, bool FUSE>
 cudaError_t dispatch_sub(int K, const Args &a)
 {
-    if (K > 32) return launch<WalkerSub<2, VALUED, MAXR>, 1, true, 24>(a);
-    if (K > 16) return launch<WalkerSub<4, VALUED, MAXR>, 1, true, 24>(a);
-    return launch<WalkerSub<8, VALUED, MAXR>, 1, true, 24>(a);
+    if (K > 32) return launch<WalkerSub<2, VALUED, MAXR, FUSE>, 1, true, 24>(a);
+    if (K > 16) return launch<WalkerSub<4, VALUED, MAXR, FUSE>, 1, true, 24>(a);
+    return launch<WalkerSub<8, VALUED, MAXR, FUSE>, 1, true, 24>(a);
 }
 
 // The row-parallel narrow walker (sequential order); long rows go to kernel B with the sub-warp walker.
-template <bool VALUED, bool MAXR>
+template <bool VALUED, bool MAXR, bool FUSE>
 cudaError_t dispatch_rows(int K, const Args &a)
 {
-    if (K > 32) return launch<WalkerRows<2, VALUED, MAXR>, 1, true, 24, WalkerSub<2, VALUED, MAXR>>(a);
-    if (K > 16) return launch<WalkerRows<4, VALUED, MAXR>, 1, true, 24, WalkerSub<4, VALUED, MAXR>>(a);
-    return launch<WalkerRows<8, VALUED, MAXR>, 1, true, 24, WalkerSub<8, VALUED, MAXR>>(a);
+    if (K > 32) return launch<WalkerRows<2, VALUED, MAXR, FUSE>, 1, true, 24, WalkerSub<2, VALUED, MAXR, FUSE>>(a);
+    if (K > 16) return launch<WalkerRows<4, VALUED, MAXR, FUSE>, 1, true, 24, WalkerSub<4, VALUED, MAXR, FUSE>>(a);
+    return launch<WalkerRows<8, VALUED, MAXR, FUSE>, 1, true, 24, WalkerSub<8, VALUED, MAXR, FUSE>>(a);
 }
 
-// Which walker sums the short rows of a product of width K on aligned operands.
-//   GESPMM_VARIANT unset / < 0 : automatic -- the sub-warp walker for K <= GESPMM_SUBWARP_MAX_K, else the ring walker
-//   0 : ring walker (the reference's sequential order for every K)   1 : register-staged walker (comparisons)
-//   2 : sub-warp walker wherever it applies (K <= 64)
-//   4 : row-parallel narrow walker wherever it applies (K <= 64; sequential order)
-constexpr int kSubwarpMaxKDefault = 64;  // measured on B200 (profiles/r01_sweep_narrow.txt): 1.1-6x the ring walker at K <= 64
-//   GESPMM_SEQUENTIAL=1 : the fastest walker that keeps the reference's order for every K (= variant 4)
-int env_variant()
+// Scalar instantiations of the register walker: any K, any alignment.
+template <bool VALUED, bool MAXR, bool FUSE>
+cudaError_t dispatch_scalar(int V, const Args &a)
 {
-    if (env_int("GESPMM_SEQUENTIAL", 0) != 0) return 4;
-    return env_int("GESPMM_VARIANT", -1);
-}
-bool use_rows(int64_t K, int variant) { return variant == 4 && K <= 64 && K % 4 == 0; }
-bool use_subwarp(int64_t K, int variant)
-{
-    if (K > 64 || K % 4 != 0) return false;
-    if (variant == 2) return true;
-    return variant < 0 && K <= env_int("GESPMM_SUBWARP_MAX_K", kSubwarpMaxKDefault);
-}
-
-// variant 1 = register-staged walker on aligned operands (kept for comparisons, GESPMM_VARIANT=1)
-template <bool VALUED, bool VEC4, bool PEER, bool MAXR>
-cudaError_t dispatch(int V, int variant, bool masked, const Args &a)
-{
-    if constexpr (!VEC4) {  // scalar instantiations: correctness path for odd K / unaligned operands
-        switch (V) {
-            case 1: return launch_reg<1, VALUED, false, 8, 16, MAXR>(a);
-            case 2: return launch_reg<2, VALUED, false, 4, 16, MAXR>(a);
-            case 3: return launch_reg<3, VALUED, false, 4, 16, MAXR>(a);
-            default: return launch_reg<4, VALUED, false, 4, 16, MAXR>(a);
-        }
-    } else {
-        if (variant == 1 && !PEER && !MAXR) {
-            switch (V) {
-                case 1: return launch_reg<1, VALUED, true, 8, 24>(a);
-                case 2: return launch_reg<2, VALUED, true, 4, 24>(a);
-                case 3: return launch_reg<3, VALUED, true, 2, 16>(a);
-                default: return launch_reg<4, VALUED, true, 2, 16>(a);
-            }
-        }
-        switch (V) {
-            case 1: return launch_default<1, VALUED, PEER, MAXR>(a, masked);
-            case 2: return launch_default<2, VALUED, PEER, MAXR>(a, masked);
-            case 3: return launch_default<3, VALUED, PEER, MAXR>(a, masked);
-            default: return launch_default<4, VALUED, PEER, MAXR>(a, masked);
-        }
+    switch (V) {
+        case 1: return launch_reg<1, VALUED, false, 8, 16, MAXR, FUSE>(a);
+        case 2: return launch_reg<2, VALUED, false, 4, 16, MAXR, FUSE>(a);
+        case 3: return launch_reg<3, VALUED, false, 4, 16, MAXR, FUSE>(a);
+        default: return launch_reg<4, VALUED, false, 4, 16, MAXR, FUSE>(a);
     }
+}
+
+// The register-staged walker on aligned operands (GESPMM_WALKER_REGISTER: comparisons, and B that lives in the L2)
+template <bool VALUED>
+cudaError_t dispatch_reg4(int V, const Args &a)
+{
+    switch (V) {
+        case 1: return launch_reg<1, VALUED, true, 8, 24>(a);
+        case 2: return launch_reg<2, VALUED, true, 4, 24>(a);
+        case 3: return launch_reg<3, VALUED, true, 2, 16>(a);
+        default: return launch_reg<4, VALUED, true, 2, 16>(a);
+    }
+}
+
+// `mode`: 0 sum, 1 max, 2 fused sum (scales / bias)
+template <bool VALUED>
+cudaError_t dispatch_all(int mode, bool vec4, bool peer, int walker, bool hint, int V, bool masked, int K, const Args &a)
+{
+    if (!vec4) {
+        if (mode == 1) return dispatch_scalar<VALUED, true, false>(V, a);
+        if (mode == 2) return dispatch_scalar<VALUED, false, true>(V, a);
+        return dispatch_scalar<VALUED, false, false>(V, a);
+    }
+    if (peer) return dispatch_ring<VALUED, true, false>(V, a, masked);
+    if (use_rows(K, walker)) {
+        if (mode == 1) return dispatch_rows<VALUED, true, false>(K, a);
+        if (mode == 2) return dispatch_rows<VALUED, false, true>(K, a);
+        return dispatch_rows<VALUED, false, false>(K, a);
+    }
+    if (use_subwarp(K, walker)) {
+        if (mode == 1) return dispatch_sub<VALUED, true, false>(K, a);
+        if (mode == 2) return dispatch_sub<VALUED, false, true>(K, a);
+        return dispatch_sub<VALUED, false, false>(K, a);
+    }
+    if (mode == 1) return dispatch_ring<VALUED, false, true>(V, a, masked);
+    if (mode == 2) return launch_ring<1, VALUED, false, false, true, false>(a, masked);  // V == 1 (see run_spmm)
+    if (walker == GESPMM_WALKER_REGISTER) return dispatch_reg4<VALUED>(V, a);
+    if (hint && V == 1) return launch_ring<1, VALUED, false, false, false, true>(a, masked);
+    return dispatch_ring<VALUED, false, false>(V, a, masked);
+}
+
+__global__ void max_row_kernel(int M, const int *__restrict__ rowptr, int *__restrict__ out)
+{
+    int best = 0;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (long long)gridDim.x * blockDim.x)
+        best = max(best, __ldg(rowptr + r + 1) - __ldg(rowptr + r));
+    best = __reduce_max_sync(kFull, best);
+    if ((threadIdx.x & 31) == 0 && best > 0) atomicMax(out, best);
 }
 
 }  // namespace
 
 namespace {
 
-// Shared by the two entry points: argument checks, task window, dispatch.  `parts` == 0: B is one array.
+// Shared by the entry points: argument checks, task window, dispatch.  `parts` == 0: B is one array.
 int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr, const int32_t *colind, const float *val,
              const float *B, int parts, const float *const *B_parts, const int64_t *part_begin, int64_t ldb, float *C,
-             int64_t ldc, void *stream, bool max_reduce = false, float init = 0.f)
+             int64_t ldc, void *stream, const gespmm_opts *opts, bool max_reduce = false, float init = 0.f)
 {
     if (M < 0 || N < 0 || K < 0 || nnz < 0) return GESPMM_ERR_INVALID_ARG;
-    if (M > INT32_MAX - 64 || N > INT32_MAX || nnz > INT32_MAX - 64 || K > INT32_MAX || ldb >= (1LL << 30) || ldc > INT32_MAX)
+    // positions are summed in int inside the kernels (p + 64 + lane, a + warp * seg, ...): keep 64 K of headroom
+    if (M > INT32_MAX - 64 || N > INT32_MAX || nnz > INT32_MAX - 65536 || K > INT32_MAX || ldb >= (1LL << 30) || ldc > INT32_MAX)
         return GESPMM_ERR_TOO_LARGE;
+    if (opts && opts->struct_size != sizeof(gespmm_opts)) return GESPMM_ERR_INVALID_ARG;
     if (M == 0 || K == 0) return GESPMM_OK;
     if (ldb < K || ldc < K) return GESPMM_ERR_INVALID_ARG;
     if (!rowptr || !C) return GESPMM_ERR_INVALID_ARG;
     if (nnz > 0 && !colind) return GESPMM_ERR_INVALID_ARG;
     if (parts == 0 && nnz > 0 && !B) return GESPMM_ERR_INVALID_ARG;
+    const Choice ch = choose(opts);
+    if (ch.fuse() && (max_reduce || parts > 0)) return GESPMM_ERR_INVALID_ARG;  // the fused scaling belongs to the plain sum
 
     bool vec4 = (K % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    if (ch.bias && (reinterpret_cast<uintptr_t>(ch.bias) & 15)) vec4 = false;
     Args a;
     a.op.peer.parts = 0;
     if (parts > 0) {
@@ -1263,13 +1600,10 @@ int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr
     // from an N x 512-byte slice of B, a quarter of the L2 footprint of a 512-column pass, and that outweighs
     // the extra colind reads on every shape measured (K = 256 / 512: Reddit 1.13x / 1.34x, R-MAT 1.14x / 1.19x,
     // cit-Patents 1.10x / 1.17x, ogbn-products 1.04x; profiles/r01_sweep_panel.txt).  Sharded B keeps wide
-    // panels (one 2 KB request per remote row instead of four).  GESPMM_PANEL_V (1..4) overrides.
+    // panels (one 2 KB request per remote row instead of four).  panel_v (1..4) overrides.
     const int max_v = packs >= 4 ? 4 : packs;
     int V = (vec4 && parts == 0) ? 1 : max_v;
-    {
-        const int forced_v = env_int("GESPMM_PANEL_V", 0);
-        if (forced_v >= 1 && forced_v <= max_v) V = forced_v;
-    }
+    if (ch.panel_v >= 1 && ch.panel_v <= max_v && !(vec4 && ch.fuse())) V = ch.panel_v;
     const bool masked = (K % (32 * W * V)) != 0;  // some lanes' packs fall beyond K
 
     // Task window (keys per task).  A task's start-up (row search, first rowptr / colind fetch) is
@@ -1277,11 +1611,8 @@ int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr
     // the average row: measured optima on B200 are ~96 keys at 5 keys/row (cit-Patents shape, at 2.5 M
     // to 20 M keys), ~256 at 21 (R-MAT), 512-1024 at ~500 (Reddit shape), i.e. ~48*sqrt(keys per row);
     // capped so that the grid keeps at least ~8 waves of resident CTAs.
-    // GESPMM_TASK / GESPMM_LONG / GESPMM_VARIANT / GESPMM_OVERLAP are tuning overrides (read per call).
-    const int forced_task = env_int("GESPMM_TASK", 0);
-    const int variant = env_variant();
-    const bool sub = vec4 && parts == 0 && use_subwarp(K, variant);
-    const bool rows_walker = vec4 && parts == 0 && use_rows(K, variant);
+    const bool sub = vec4 && parts == 0 && use_subwarp(K, ch.walker);
+    const bool rows_walker = vec4 && parts == 0 && use_rows(K, ch.walker);
     const long long total = nnz + M;
     const long long warps_per_wave = 148LL * 24;
     const double keys_per_row = (double)total / (double)M;
@@ -1292,48 +1623,91 @@ int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr
     const long long cap = (total / (8 * warps_per_wave)) & ~31LL;
     if (tk > cap) tk = cap;
     int task = (int)(tk < 32 ? 32 : (tk > kMaxTask ? kMaxTask : tk));
-    if (forced_task >= 32 && forced_task <= kMaxTask) task = forced_task & ~31;
-    const int long_row = long_row_threshold();
+    if (ch.task >= 32 && ch.task <= kMaxTask) task = ch.task & ~31;
 
-    a.M = (int)M; a.K = (int)K; a.task = task; a.long_row = long_row; a.nnz = nnz; a.rowptr = rowptr;
+    a.M = (int)M; a.K = (int)K; a.task = task; a.long_row = ch.long_row; a.nnz = nnz; a.rowptr = rowptr;
     a.op.colind = colind; a.op.val = val; a.op.B = B; a.op.C = C; a.op.ldb = (int)ldb; a.op.ldc = (int)ldc;
     a.st = static_cast<cudaStream_t>(stream);
-    a.overlap = env_int("GESPMM_OVERLAP", 1) != 0;
+    a.overlap = ch.overlap;
+    a.has_long = nnz > ch.long_row && (ch.max_row_nnz < 0 || ch.max_row_nnz > ch.long_row);
+    a.smem_pad = ch.smem_pad;
     a.op.init = init;
-    cudaError_t err;
-    if (rows_walker) {
-        if (max_reduce) err = val ? dispatch_rows<true, true>((int)K, a) : dispatch_rows<false, true>((int)K, a);
-        else err = val ? dispatch_rows<true, false>((int)K, a) : dispatch_rows<false, false>((int)K, a);
-    } else if (sub) {
-        if (max_reduce) err = val ? dispatch_sub<true, true>((int)K, a) : dispatch_sub<false, true>((int)K, a);
-        else err = val ? dispatch_sub<true, false>((int)K, a) : dispatch_sub<false, false>((int)K, a);
-    } else if (max_reduce) {
-        if (val) err = vec4 ? dispatch<true, true, false, true>(V, 0, masked, a) : dispatch<true, false, false, true>(V, 0, masked, a);
-        else err = vec4 ? dispatch<false, true, false, true>(V, 0, masked, a) : dispatch<false, false, false, true>(V, 0, masked, a);
-    } else if (parts > 0) {
-        err = val ? dispatch<true, true, true, false>(V, 0, masked, a) : dispatch<false, true, true, false>(V, 0, masked, a);
-    } else if (val) {
-        err = vec4 ? dispatch<true, true, false, false>(V, variant, masked, a) : dispatch<true, false, false, false>(V, variant, masked, a);
-    } else {
-        err = vec4 ? dispatch<false, true, false, false>(V, variant, masked, a) : dispatch<false, false, false, false>(V, variant, masked, a);
-    }
+    a.op.row_scale = ch.row_scale; a.op.col_scale = ch.col_scale; a.op.bias = ch.bias;
+    a.op.l2_near = ch.l2_policy & 3; a.op.l2_far = (ch.l2_policy >> 2) & 3; a.op.l2_store = (ch.l2_policy >> 4) & 3;
+    a.op.l2_window = ch.l2_window;
+    const int mode = max_reduce ? 1 : (ch.fuse() ? 2 : 0);
+    const bool hint = ch.l2_policy > 0 && mode == 0;
+    const cudaError_t err = val ? dispatch_all<true>(mode, vec4, parts > 0, ch.walker, hint, V, masked, (int)K, a)
+                                : dispatch_all<false>(mode, vec4, parts > 0, ch.walker, hint, V, masked, (int)K, a);
     return err == cudaSuccess ? GESPMM_OK : GESPMM_ERR_CUDA;
 }
 
+int sequential_for(int64_t K, int64_t row_nnz, const Choice &ch)
+{
+    if (row_nnz > ch.long_row) return 0;  // segmented (kernel B)
+    if (row_nnz > 1 && use_subwarp(K, ch.walker) && !use_rows(K, ch.walker)) return 0;  // per-group partial sums
+    return 1;
+}
+
 }  // namespace
+
+extern "C" void gespmm_opts_init(gespmm_opts *opts)
+{
+    if (!opts) return;
+    memset(opts, 0, sizeof(*opts));
+    opts->struct_size = (uint32_t)sizeof(*opts);
+    opts->max_row_nnz = -1;
+}
+
+extern "C" void gespmm_reload_env(void)
+{
+    tuning();  // the once-flag is spent first, so that a concurrent first call cannot overwrite the fresh values
+    g_tuning = read_env();
+}
 
 extern "C" int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr,
                                    const int32_t *colind, const float *val, const float *B, int64_t ldb,
                                    float *C, int64_t ldc, void *stream)
 {
-    return run_spmm(M, N, K, nnz, rowptr, colind, val, B, 0, nullptr, nullptr, ldb, C, ldc, stream);
+    return run_spmm(M, N, K, nnz, rowptr, colind, val, B, 0, nullptr, nullptr, ldb, C, ldc, stream, nullptr);
 }
 
-extern "C" int gespmm_row_sum_is_sequential(int64_t K, int64_t row_nnz)
+extern "C" int gespmm_csr_spmm_f32_ex(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr,
+                                      const int32_t *colind, const float *val, const float *B, int64_t ldb,
+                                      float *C, int64_t ldc, const gespmm_opts *opts, void *stream)
 {
-    if (row_nnz > long_row_threshold()) return 0;  // segmented (kernel B)
-    if (row_nnz > 1 && use_subwarp(K, env_variant())) return 0;                         // per-group partial sums
-    return 1;
+    return run_spmm(M, N, K, nnz, rowptr, colind, val, B, 0, nullptr, nullptr, ldb, C, ldc, stream, opts);
+}
+
+extern "C" int gespmm_max_row_nnz(int64_t M, const int32_t *rowptr, int32_t *out_host, void *stream)
+{
+    if (M < 0 || M > INT32_MAX - 64 || !out_host || (M > 0 && !rowptr)) return GESPMM_ERR_INVALID_ARG;
+    *out_host = 0;
+    if (M == 0) return GESPMM_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int *d = nullptr;
+    if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) { cudaGetLastError(); return GESPMM_ERR_CUDA; }
+    int rc = GESPMM_ERR_CUDA;
+    do {
+        if (cudaMemsetAsync(d, 0, sizeof(int), st) != cudaSuccess) break;
+        const int blocks = (int)((M + 255) / 256 < 148 * 8 ? (M + 255) / 256 : 148 * 8);
+        max_row_kernel<<<blocks, 256, 0, st>>>((int)M, rowptr, d);
+        if (cudaGetLastError() != cudaSuccess) break;
+        if (cudaMemcpyAsync(out_host, d, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+        if (cudaStreamSynchronize(st) != cudaSuccess) break;
+        rc = GESPMM_OK;
+    } while (0);
+    if (rc != GESPMM_OK) cudaGetLastError();
+    cudaFree(d);
+    return rc;
+}
+
+extern "C" int gespmm_row_sum_is_sequential(int64_t K, int64_t row_nnz) { return sequential_for(K, row_nnz, choose(nullptr)); }
+
+extern "C" int gespmm_row_sum_is_sequential_ex(int64_t K, int64_t row_nnz, const gespmm_opts *opts)
+{
+    if (opts && opts->struct_size != sizeof(gespmm_opts)) return 0;
+    return sequential_for(K, row_nnz, choose(opts));
 }
 
 extern "C" int gespmm_csr_spmm_f32_bparts(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr,
@@ -1341,12 +1715,12 @@ extern "C" int gespmm_csr_spmm_f32_bparts(int64_t M, int64_t N, int64_t K, int64
                                           const int64_t *part_begin, int64_t ldb, float *C, int64_t ldc, void *stream)
 {
     if (parts < 1) return GESPMM_ERR_INVALID_ARG;
-    return run_spmm(M, N, K, nnz, rowptr, colind, val, nullptr, parts, B_parts, part_begin, ldb, C, ldc, stream);
+    return run_spmm(M, N, K, nnz, rowptr, colind, val, nullptr, parts, B_parts, part_begin, ldb, C, ldc, stream, nullptr);
 }
 
 extern "C" int gespmm_csr_spmm_max_f32(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr,
                                        const int32_t *colind, const float *val, const float *B, int64_t ldb,
                                        float *C, int64_t ldc, float init, void *stream)
 {
-    return run_spmm(M, N, K, nnz, rowptr, colind, val, B, 0, nullptr, nullptr, ldb, C, ldc, stream, true, init);
+    return run_spmm(M, N, K, nnz, rowptr, colind, val, B, 0, nullptr, nullptr, ldb, C, ldc, stream, nullptr, true, init);
 }

@@ -34,7 +34,8 @@ void check_float(const torch::Tensor &t, const char *name, int dim)
     TORCH_CHECK(t.dim() == dim, name, " must be ", dim, "-D");
 }
 
-torch::Tensor run(const torch::Tensor &rowptr, const torch::Tensor &colind, const float *val, const torch::Tensor &B)
+torch::Tensor run(const torch::Tensor &rowptr, const torch::Tensor &colind, const float *val, const torch::Tensor &B,
+                  const gespmm_opts *opts = nullptr)
 {
     TORCH_CHECK(rowptr.size(0) >= 1, "A_rowptr must have at least one element");
     TORCH_CHECK(rowptr.device() == B.device() && colind.device() == B.device(), "all tensors must be on B's device");
@@ -42,10 +43,19 @@ torch::Tensor run(const torch::Tensor &rowptr, const torch::Tensor &colind, cons
     c10::cuda::CUDAGuard guard(B.device());
     auto out = torch::empty({M, K}, B.options());  // spmm_kernel.cu:182-184
     cudaStream_t stream = at::cuda::getCurrentCUDAStream();
-    const int rc = gespmm_csr_spmm_f32(M, N, K, nnz, rowptr.data_ptr<int>(), colind.data_ptr<int>(), val,
-                                       B.data_ptr<float>(), K, out.data_ptr<float>(), K, stream);
+    const int rc = gespmm_csr_spmm_f32_ex(M, N, K, nnz, rowptr.data_ptr<int>(), colind.data_ptr<int>(), val,
+                                          B.data_ptr<float>(), K, out.data_ptr<float>(), K, opts, stream);
     TORCH_CHECK(rc == GESPMM_OK, "gespmm_csr_spmm_f32 failed: ", gespmm_error_string(rc));
     return out;
+}
+
+const float *optional_vector(const c10::optional<torch::Tensor> &t, const char *name, int64_t len, const torch::Tensor &B)
+{
+    if (!t.has_value() || !t->defined()) return nullptr;
+    check_float(*t, name, t->dim());
+    TORCH_CHECK(t->numel() == len, name, " must have ", len, " elements");
+    TORCH_CHECK(t->device() == B.device(), "all tensors must be on B's device");
+    return t->data_ptr<float>();
 }
 
 }  // namespace
@@ -95,10 +105,55 @@ torch::Tensor csr2csc(torch::Tensor rowptr, torch::Tensor colind, torch::Tensor 
     return csc_val;
 }
 
+// New (no reference counterpart): the product with per-call options -- summation order, the graph's longest row
+// (lets the call skip the long-row kernel), and GCNConv's normalisation / bias passes (pytorch-custom/op.py:142-147)
+// fused into the kernel:  out = (A @ (B * col_scale[:, None])) * row_scale[:, None] + bias, bit-identical to the
+// four separate passes.  A_csrVal / row_scale / col_scale / bias may be None.
+torch::Tensor csr_spmm_ex(torch::Tensor A_rowptr, torch::Tensor A_colind, c10::optional<torch::Tensor> A_csrVal,
+                          torch::Tensor B, bool sequential, int64_t max_row_nnz, c10::optional<torch::Tensor> row_scale,
+                          c10::optional<torch::Tensor> col_scale, c10::optional<torch::Tensor> bias)
+{
+    check_index(A_rowptr, "A_rowptr");
+    check_index(A_colind, "A_colind");
+    check_float(B, "B", 2);
+    const float *val = nullptr;
+    if (A_csrVal.has_value() && A_csrVal->defined()) {
+        check_float(*A_csrVal, "A_csrVal", 1);
+        TORCH_CHECK(A_csrVal->size(0) == A_colind.size(0), "A_csrVal and A_colind must have the same length");
+        TORCH_CHECK(A_csrVal->device() == B.device(), "all tensors must be on B's device");
+        val = A_csrVal->data_ptr<float>();
+    }
+    gespmm_opts o;
+    gespmm_opts_init(&o);
+    if (sequential) o.flags |= GESPMM_FLAG_SEQUENTIAL;
+    o.max_row_nnz = max_row_nnz;
+    o.row_scale = optional_vector(row_scale, "row_scale", A_rowptr.size(0) - 1, B);
+    o.col_scale = optional_vector(col_scale, "col_scale", B.size(0), B);
+    o.bias = optional_vector(bias, "bias", B.size(1), B);
+    return run(A_rowptr, A_colind, val, B, &o);
+}
+
+// Longest row of a CSR on the device (one small kernel + a 4-byte copy back; synchronises the current stream).
+int64_t max_row_nnz(torch::Tensor rowptr)
+{
+    check_index(rowptr, "rowptr");
+    TORCH_CHECK(rowptr.size(0) >= 1, "rowptr must have at least one element");
+    c10::cuda::CUDAGuard guard(rowptr.device());
+    int32_t out = 0;
+    const int rc = gespmm_max_row_nnz(rowptr.size(0) - 1, rowptr.data_ptr<int>(), &out, at::cuda::getCurrentCUDAStream());
+    TORCH_CHECK(rc == GESPMM_OK, "gespmm_max_row_nnz failed: ", gespmm_error_string(rc));
+    return out;
+}
+
 PYBIND11_MODULE(spmm, m)
 {
     m.doc() = "spmm in CSR format. csr_spmm is the kernel with edge value. csr2csc provides the format transformation";
     m.def("csr_spmm", &csr_spmm, "CSR SPMM");
     m.def("csr_spmm_no_edge_value", &csr_spmm_no_edge_value, "CSR SPMM NO EDGE VALUE");
     m.def("csr2csc", &csr2csc, "csr2csc");
+    m.def("csr_spmm_ex", &csr_spmm_ex, "CSR SPMM with per-call options and fused row / column scaling and bias",
+          pybind11::arg("A_rowptr"), pybind11::arg("A_colind"), pybind11::arg("A_csrVal"), pybind11::arg("B"),
+          pybind11::arg("sequential") = false, pybind11::arg("max_row_nnz") = -1, pybind11::arg("row_scale") = pybind11::none(),
+          pybind11::arg("col_scale") = pybind11::none(), pybind11::arg("bias") = pybind11::none());
+    m.def("max_row_nnz", &max_row_nnz, "longest row of a device CSR");
 }

@@ -16,6 +16,10 @@
  *                                  spmmWrapper (spmm_test.cu:456-492) and spmm_test0..4<T>
  *                                  (spmm_test.cu:64-454);  XTopoCsrmm<float>
  *                                  (dgl-custom/binary_reduce_sum.cu:309-335) has the same shape.
+ *   gespmm_csr_spmm_f32_ex         the same launch blocks plus the element-wise passes GCNConv.forward runs
+ *                                  around them (pytorch-custom/op.py:142-147: x * out_deg_norm, * in_deg_norm, + bias),
+ *                                  fused; per-call summation order instead of a process-wide switch
+ *   gespmm_max_row_nnz             no reference counterpart (per-graph figure that lets a call skip the long-row kernel)
  *   gespmm_csr_spmm_max_f32        topo*SPMMMaxKernel / XTopoCsrmmmax<float>
  *                                  (dgl-custom/binary_reduce_max.cu:26-204)
  *   gespmm_csr2csc_f32             csr2cscKernel / csr2csc_cuda
@@ -118,6 +122,70 @@ int gespmm_csr_spmm_f32_bparts(int64_t M, int64_t N, int64_t K, int64_t nnz,
 int gespmm_csr_spmm_max_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
                             const int32_t *rowptr, const int32_t *colind, const float *val,
                             const float *B, int64_t ldb, float *C, int64_t ldc, float init, void *stream);
+
+/*
+ * Per-call options of the product (gespmm_csr_spmm_f32_ex).  Everything a caller could previously only choose
+ * through process-wide GESPMM_* environment variables is a field here, so that a library embedded in a
+ * trainer can pick the summation order (or fuse its normalisation) per call and per thread.
+ * Initialise with gespmm_opts_init(), then set fields; unknown / zero fields mean "automatic".
+ */
+#define GESPMM_FLAG_SEQUENTIAL  0x1u  /* sum every row of at most GESPMM_LONG_ROW nonzeros in strictly sequential CSR
+                                         order for every K (bit-identical to the reference kernels); without it the
+                                         faster re-associating sub-warp walker is used for K <= 64 */
+#define GESPMM_FLAG_NO_OVERLAP  0x2u  /* run the long-row kernel on `stream` itself, not on the helper stream */
+
+/* values of gespmm_opts.walker (tuning / comparisons; 0 = automatic) */
+#define GESPMM_WALKER_AUTO      0
+#define GESPMM_WALKER_RING      1     /* cp.async gather ring, one nonzero per warp-wide copy, sequential order */
+#define GESPMM_WALKER_REGISTER  2     /* register-staged gathers (no shared memory), sequential order           */
+#define GESPMM_WALKER_SUBWARP   3     /* K <= 64: 2 / 4 / 8 nonzeros per warp-wide copy, re-associated           */
+#define GESPMM_WALKER_ROWS      4     /* K <= 64: lane groups own disjoint rows, sequential order                */
+
+typedef struct gespmm_opts {
+    uint32_t struct_size;    /* sizeof(gespmm_opts), set by gespmm_opts_init (ABI versioning)                    */
+    uint32_t flags;          /* GESPMM_FLAG_*                                                                    */
+    int64_t  max_row_nnz;    /* longest row of A if the caller knows it (gespmm_max_row_nnz), else -1: when it is
+                                <= the long-row threshold the long-row kernel is not launched at all            */
+    /* Fused epilogue / prologue of a GCN layer (pytorch-custom/op.py:142-147), all device pointers, all nullable:
+     *   C[r, c] = (sum_p val[p] * (B[colind[p], c] * col_scale[colind[p]])) * row_scale[r] + bias[c]
+     * Every product and sum is a separately rounded fp32 operation in exactly this order, so the result is
+     * bit-identical to scaling B, running the plain product, scaling C and adding the bias in four passes. */
+    const float *row_scale;  /* [M]  */
+    const float *col_scale;  /* [N]  */
+    const float *bias;       /* [K]  */
+    int32_t  walker;         /* GESPMM_WALKER_*                                                                  */
+    int32_t  task_keys;      /* keys (rows + nonzeros) per task of the main kernel, multiple of 32 in [32, 1024]  */
+    int32_t  long_row;       /* long-row threshold override, [512, 2^20]                                         */
+    int32_t  panel_v;        /* 128-column blocks per pass (1..4)                                                */
+    int32_t  l2_policy;      /* experimental: L2 eviction-priority steering of the B gathers, see DESIGN.md 3.5  */
+    int32_t  l2_window_rows; /* experimental: |col - row| below which a gathered row counts as "near"            */
+} gespmm_opts;
+
+void gespmm_opts_init(gespmm_opts *opts);
+
+/* gespmm_csr_spmm_f32 with per-call options (opts == NULL: exactly gespmm_csr_spmm_f32). */
+int gespmm_csr_spmm_f32_ex(int64_t M, int64_t N, int64_t K, int64_t nnz,
+                           const int32_t *rowptr, const int32_t *colind, const float *val,
+                           const float *B, int64_t ldb, float *C, int64_t ldc,
+                           const gespmm_opts *opts, void *stream);
+
+/*
+ * Longest row of a device CSR: *out_host = max_r (rowptr[r+1] - rowptr[r]).  One small reduction kernel and a
+ * 4-byte copy back; synchronises `stream`.  A per-graph quantity: compute it once, pass it in
+ * gespmm_opts.max_row_nnz on every product over that graph (optional caller-owned plan).
+ */
+int gespmm_max_row_nnz(int64_t M, const int32_t *rowptr, int32_t *out_host, void *stream);
+
+/*
+ * The GESPMM_* tuning environment variables (GESPMM_TASK, GESPMM_LONG, GESPMM_VARIANT, GESPMM_SEQUENTIAL,
+ * GESPMM_PANEL_V, GESPMM_OVERLAP, GESPMM_SUBWARP_MAX_K, GESPMM_L2_POLICY, GESPMM_L2_WINDOW) are read ONCE, at the first call
+ * into the library; per-call choices belong in gespmm_opts.  gespmm_reload_env re-reads them (sweep
+ * scripts and tests that change the environment of a running process; not thread-safe against concurrent calls).
+ */
+void gespmm_reload_env(void);
+
+/* gespmm_row_sum_is_sequential for a call made with `opts` (NULL: same as the plain function). */
+int gespmm_row_sum_is_sequential_ex(int64_t K, int64_t row_nnz, const gespmm_opts *opts);
 
 /* Enable reads of `peer_device`'s memory from kernels on the current device (idempotent). */
 int gespmm_enable_peer_access(int peer_device);

@@ -32,6 +32,16 @@ for step in $STEPS; do
     oddk)     # class-count widths (K % 4 != 0: the scalar walker) next to the reference's kernels for K < 64
       timeout 600 python scripts/sweep_narrow.py --workloads products,citpatents --Ks 3,7,41,47 --variants -1 --tasks 0 --valued 1,0 --ref > $O/sweep_oddk.txt 2> $O/sweep_oddk.err
       note "oddk rc=$?" ;;
+    uniform)  # the uniformly-random variant of the cit-Patents shape: time + DRAM bytes per launch
+      timeout 300 python bench.py --workload citpatents_uniform --no-cpu --no-e2e --steps 50 > $O/bench_uniform.json 2> $O/bench_uniform.err; note "uniform rc=$?"
+      for wl in citpatents citpatents_uniform; do
+        timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,lts__t_sectors_op_read.sum,lts__t_sectors_op_write.sum,lts__t_sectors_srcunit_tex_op_read_lookup_hit.sum,lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum \
+            --clock-control none -k regex:spmm_ --launch-skip 6 -c 2 --csv --log-file $O/ncu_dram_$wl.csv \
+            python bench.py --workload $wl --steps 3 --warmup 3 --no-cpu --no-e2e --no-ref-kernel > $O/ncu_dram_$wl.log 2>&1
+        note "ncu dram $wl rc=$?"
+      done ;;
+    regreddit) # register-staged walker (GESPMM_VARIANT=1) next to the ring walker where B is L2-resident
+      timeout 400 python scripts/sweep_narrow.py --workloads reddit,products --Ks 128,256 --variants -1,1 --tasks 0 --valued 0,1 > $O/sweep_regreddit.txt 2> $O/sweep_regreddit.err; note "regreddit rc=$?" ;;
     rows)     # sub-warp (2) vs row-parallel (4) narrow walkers on every shape
       timeout 600 python scripts/sweep_narrow.py --variants 2,4 --tasks 0 > $O/sweep_v24.txt 2> $O/sweep_v24.err; note "rows rc=$?" ;;
     auto64)   # the SpMM suite with the sub-warp walker chosen automatically for K <= 64

@@ -22,6 +22,31 @@ def pkg():
     return entry.load_package()
 
 
+class _TuningEnv:
+    """The GESPMM_* environment is read once by the library (include/gespmm.h: gespmm_reload_env); tests that change
+    it mid-process go through this helper, which re-reads it after every change and restores it afterwards."""
+
+    def __init__(self, monkeypatch):
+        from gespmm_b200 import capi
+        self._mp, self._capi = monkeypatch, capi
+
+    def setenv(self, name, value):
+        self._mp.setenv(name, value)
+        self._capi.reload_env()
+
+    def delenv(self, name, raising=True):
+        self._mp.delenv(name, raising=raising)
+        self._capi.reload_env()
+
+
+@pytest.fixture
+def gespmm_env(pkg, monkeypatch):
+    env = _TuningEnv(monkeypatch)
+    yield env
+    monkeypatch.undo()
+    env._capi.reload_env()
+
+
 @pytest.fixture(scope="session")
 def oracle():
     o = entry.load_oracle()

@@ -88,32 +88,56 @@ def test_argument_validation_without_a_device(pkg):
             capi.csr_spmm_host(rp, np.zeros(0, np.int32), None, B)
 
 
-def test_row_sum_order_query(pkg, monkeypatch):
+def test_row_sum_order_query(pkg, gespmm_env):
     """gespmm_row_sum_is_sequential is a pure function of (K, row length) and the tuning environment."""
     from gespmm_b200 import capi
     for name in ("GESPMM_VARIANT", "GESPMM_SUBWARP_MAX_K", "GESPMM_LONG", "GESPMM_SEQUENTIAL"):
-        monkeypatch.delenv(name, raising=False)
+        gespmm_env.delenv(name, raising=False)
     for K in (1, 4, 32, 64, 100, 128, 512, 4096):
         assert capi.row_sum_is_sequential(K, 0) and capi.row_sum_is_sequential(K, 1)
         assert not capi.row_sum_is_sequential(K, capi.LONG_ROW + 1)
         assert capi.row_sum_is_sequential(K, capi.LONG_ROW) == capi.row_sum_is_sequential(K, 2)
     assert capi.row_sum_is_sequential(128, capi.LONG_ROW) and capi.row_sum_is_sequential(68, 2) and capi.row_sum_is_sequential(30, 2)
-    monkeypatch.setenv("GESPMM_VARIANT", "0")  # the ring walker: sequential for every K
+    gespmm_env.setenv("GESPMM_VARIANT", "0")  # the ring walker: sequential for every K
     assert all(capi.row_sum_is_sequential(K, capi.LONG_ROW) for K in (4, 16, 32, 64))
-    monkeypatch.setenv("GESPMM_VARIANT", "2")  # the sub-warp walker wherever it applies: K <= 64, K % 4 == 0
+    gespmm_env.setenv("GESPMM_VARIANT", "2")  # the sub-warp walker wherever it applies: K <= 64, K % 4 == 0
     assert not any(capi.row_sum_is_sequential(K, 2) for K in (4, 16, 32, 48, 64))
     assert all(capi.row_sum_is_sequential(K, 2) for K in (3, 30, 65, 68, 128))
-    monkeypatch.setenv("GESPMM_VARIANT", "4")  # the row-parallel narrow walker: sequential again
+    gespmm_env.setenv("GESPMM_VARIANT", "4")  # the row-parallel narrow walker: sequential again
     assert all(capi.row_sum_is_sequential(K, capi.LONG_ROW) for K in (4, 16, 32, 48, 64, 128))
-    monkeypatch.setenv("GESPMM_VARIANT", "2")
-    monkeypatch.setenv("GESPMM_SEQUENTIAL", "1")  # wins over GESPMM_VARIANT
+    gespmm_env.setenv("GESPMM_VARIANT", "2")
+    gespmm_env.setenv("GESPMM_SEQUENTIAL", "1")  # wins over GESPMM_VARIANT
     assert all(capi.row_sum_is_sequential(K, capi.LONG_ROW) for K in (4, 16, 32, 48, 64, 128))
-    monkeypatch.delenv("GESPMM_SEQUENTIAL")
-    monkeypatch.delenv("GESPMM_VARIANT")
-    monkeypatch.setenv("GESPMM_SUBWARP_MAX_K", "32")
+    gespmm_env.delenv("GESPMM_SEQUENTIAL")
+    gespmm_env.delenv("GESPMM_VARIANT")
+    gespmm_env.setenv("GESPMM_SUBWARP_MAX_K", "32")
     assert not capi.row_sum_is_sequential(32, 2) and capi.row_sum_is_sequential(64, 2)
-    monkeypatch.setenv("GESPMM_LONG", "1024")
+    gespmm_env.setenv("GESPMM_LONG", "1024")
     assert not capi.row_sum_is_sequential(128, 1025) and capi.row_sum_is_sequential(128, 1024)
+
+
+def test_per_call_options_override_the_environment(pkg, gespmm_env):
+    """gespmm_opts carries per call what used to be process-wide: the summation order and the tuning knobs; the
+    environment is read once and only re-read by gespmm_reload_env."""
+    import os
+    from gespmm_b200 import capi
+    for name in ("GESPMM_VARIANT", "GESPMM_SUBWARP_MAX_K", "GESPMM_LONG", "GESPMM_SEQUENTIAL"):
+        gespmm_env.delenv(name, raising=False)
+    o = capi.opts()
+    assert o.struct_size == __import__("ctypes").sizeof(capi.Opts) and o.max_row_nnz == -1 and o.flags == 0
+    assert not capi.row_sum_is_sequential(32, 2)                      # default at K <= 64: the sub-warp walker
+    assert capi.row_sum_is_sequential(32, 2, capi.opts(sequential=True))
+    assert capi.row_sum_is_sequential(32, capi.LONG_ROW, capi.opts(walker=capi.WALKER_RING))
+    assert not capi.row_sum_is_sequential(128, 2000, capi.opts(long_row=1024))
+    gespmm_env.setenv("GESPMM_VARIANT", "0")                          # environment says ring ...
+    assert not capi.row_sum_is_sequential(32, 2, capi.opts(walker=capi.WALKER_SUBWARP))   # ... the call says sub-warp
+    os.environ["GESPMM_VARIANT"] = "2"                                # changed behind the library's back: not seen ...
+    assert capi.row_sum_is_sequential(32, 2)
+    capi.reload_env()                                                 # ... until it is told to look again
+    assert not capi.row_sum_is_sequential(32, 2)
+    bad = capi.opts()
+    bad.struct_size = 8                                               # an opts struct of another ABI version is refused
+    assert not capi.row_sum_is_sequential(32, 1, bad)
 
 
 # ---- .mtx reader -----------------------------------------------------------------------------------
@@ -282,13 +306,17 @@ def test_mtx_writer_roundtrip(pkg, tmp_path, golden_csr):
 
 def test_operator_module_surface(pkg):
     from gespmm_b200 import op
-    assert sorted(n for n in dir(op.spmm) if not n.startswith("_")) == ["csr2csc", "csr_spmm", "csr_spmm_no_edge_value"]
+    names = sorted(n for n in dir(op.spmm) if not n.startswith("_"))
+    assert [n for n in names if n not in ("csr_spmm_ex", "max_row_nnz")] == ["csr2csc", "csr_spmm", "csr_spmm_no_edge_value"]  # spmm.cpp:96-101
+    assert "csr_spmm_ex" in names and "max_row_nnz" in names  # the additions: per-call options, fused scaling
     assert op.spmm.__doc__.startswith("spmm in CSR format")  # spmm.cpp:97
     rp = torch.zeros(5, dtype=torch.int32); ci = torch.zeros(0, dtype=torch.int32); B = torch.zeros(4, 8)
     with pytest.raises(RuntimeError, match="CUDA"):  # reference: C assert -> abort; here: exception, and no CPU path
         op.spmm.csr_spmm_no_edge_value(rp, ci, B)
     with pytest.raises(RuntimeError, match="CUDA"):
         op.spmm.csr_spmm(rp, ci, torch.zeros(0), B)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        op.spmm.csr_spmm_ex(rp, ci, None, B, sequential=True, row_scale=torch.zeros(4))
     conv = op.GCNConv(16, 8)
     assert repr(conv) == "GCNConv(16, 8)" and conv.weight.shape == (16, 8) and conv.bias.abs().sum() == 0
     assert conv.weight.abs().max() <= (6.0 / 24) ** 0.5 + 1e-6

@@ -189,13 +189,13 @@ def test_long_rows_segmented_path(spmm, dev, oracle, K):
 
 
 @pytest.mark.parametrize("K", [4, 8, 12, 16, 20, 24, 32, 36, 48, 60, 64])
-def test_subwarp_walker_for_narrow_B(spmm, dev, oracle, pkg, monkeypatch, K):
+def test_subwarp_walker_for_narrow_B(spmm, dev, oracle, pkg, gespmm_env, K):
     """GESPMM_VARIANT=2: 2 / 4 / 8 nonzeros per warp-wide gather for K <= 64 / 32 / 16.  Integer-valued operands make
     every fp32 sum exact, so the result must equal the oracle bit for bit whatever the association; real-valued
     operands must stay within 1e-4 of the fp64 golden, be deterministic, and rows of <= 1 nonzero stay bit-exact.
     Empty rows, rows ending at every position of a quad, long (> 4096) and huge (>= 32768) rows, max-reduce."""
     from gespmm_b200 import capi
-    monkeypatch.setenv("GESPMM_VARIANT", "2")
+    gespmm_env.setenv("GESPMM_VARIANT", "2")
     assert not capi.row_sum_is_sequential(K, 2) and capi.row_sum_is_sequential(K, 1)
     assert capi.row_sum_is_sequential(128, LONG)  # wider products are not affected
     rng = np.random.default_rng(500 + K)
@@ -226,7 +226,7 @@ def test_subwarp_walker_for_narrow_B(spmm, dev, oracle, pkg, monkeypatch, K):
         torch.cuda.synchronize()
         assert np.array_equal(C.cpu().numpy(), oracle.spmm_max(rowptr, colind, None if vv is None else vf, Bf, init=-10000.0))
     # not a multiple of 4 / unaligned: the request is ignored, the sequential scalar walker runs
-    monkeypatch.setenv("GESPMM_VARIANT", "2")
+    gespmm_env.setenv("GESPMM_VARIANT", "2")
     B3 = rng.standard_normal((N, K - 1)).astype(np.float32)
     C = _run(spmm, dev, rowptr, colind, None, B3).cpu().numpy()
     want = oracle.spmm(rowptr, colind, None, B3)
@@ -235,12 +235,12 @@ def test_subwarp_walker_for_narrow_B(spmm, dev, oracle, pkg, monkeypatch, K):
 
 
 @pytest.mark.parametrize("K", [4, 8, 16, 24, 32, 36, 48, 64])
-def test_row_parallel_walker_for_narrow_B_is_sequential(spmm, dev, oracle, pkg, monkeypatch, K):
+def test_row_parallel_walker_for_narrow_B_is_sequential(spmm, dev, oracle, pkg, gespmm_env, K):
     """GESPMM_VARIANT=4: the lane groups own disjoint rows, each summed in CSR order -- bit-identical to the oracle
     (real-valued operands) on every row up to GESPMM_LONG_ROW, whatever the balance of the 32-row runs: empty rows,
     single-row runs between long rows, rows much longer than their neighbours; max-reduce bit-identical everywhere."""
     from gespmm_b200 import capi
-    monkeypatch.setenv("GESPMM_VARIANT", "4")
+    gespmm_env.setenv("GESPMM_VARIANT", "4")
     assert capi.row_sum_is_sequential(K, LONG) and not capi.row_sum_is_sequential(K, LONG + 1)
     rng = np.random.default_rng(700 + K)
     M, N = 2600, 3000
