@@ -396,6 +396,16 @@ __device__ __forceinline__ void cp_async16_hint(unsigned saddr, const void *g, u
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async4(unsigned saddr, const void *g)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ float lds32(unsigned saddr)
+{
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(r) : "r"(saddr) : "memory");
+    return r;
+}
 __device__ __forceinline__ float4 lds128(unsigned saddr)
 {
     float4 r;
@@ -451,6 +461,7 @@ struct WalkerRing {
     // HINT
     unsigned long long pol_near, pol_far, pol_store;
     int window, cur_row;
+    bool hint_gather, hint_store;  // a priority code of 0 everywhere = the plain instruction (no descriptor)
 
     static constexpr int kPanel = 128 * V;
     __device__ __forceinline__ void init(const Operands &o, int panel, int K, int ln, unsigned ring_base) {
@@ -473,6 +484,7 @@ struct WalkerRing {
         if constexpr (HINT) {
             pol_near = l2_policy(o.l2_near); pol_far = l2_policy(o.l2_far); pol_store = l2_policy(o.l2_store);
             window = o.l2_window; cur_row = 0;
+            hint_gather = (o.l2_near | o.l2_far) != 0; hint_store = o.l2_store != 0;
         }
     }
     __device__ __forceinline__ void finish(T (&)[V]) const {}
@@ -514,8 +526,10 @@ struct WalkerRing {
         for (int v = 0; v < V; v++) {
             if (pack_on(v)) {
                 const T out = FUSE ? E::apply(acc[v], rs, bias_v[v], has_bias) : acc[v];
-                if constexpr (HINT) st_hint_f4(c + v * kStride, out, pol_store);
-                else P::stcs(c + v * kStride, out);
+                if constexpr (HINT) {
+                    if (hint_store) st_hint_f4(c + v * kStride, out, pol_store);
+                    else P::stcs(c + v * kStride, out);
+                } else P::stcs(c + v * kStride, out);
             }
         }
     }
@@ -545,8 +559,10 @@ struct WalkerRing {
 #pragma unroll
                     for (int v = 0; v < V; v++) {
                         if (pack_on(v)) {
-                            if constexpr (HINT) cp_async16_hint(ring + slot + ((i0 + i) * V + v) * 512, bp[i] + v * 512, pol[i]);
-                            else cp_async16<CP>(ring + slot + ((i0 + i) * V + v) * 512, bp[i] + v * 512);
+                            if constexpr (HINT) {
+                                if (hint_gather) cp_async16_hint(ring + slot + ((i0 + i) * V + v) * 512, bp[i] + v * 512, pol[i]);
+                                else cp_async16<CP>(ring + slot + ((i0 + i) * V + v) * 512, bp[i] + v * 512);
+                            } else cp_async16<CP>(ring + slot + ((i0 + i) * V + v) * 512, bp[i] + v * 512);
                         }
                     }
                 }
@@ -661,10 +677,13 @@ struct WalkerRing {
 // (group g with g ^ NG/2, then ^ NG/4, ...) and group 0 stores the row.  Deterministic, but NOT the
 // reference's strictly sequential order: results differ from it by fp32 re-association (max-reduce:
 // still bit-identical).  gespmm_row_sum_is_sequential() tells callers which rows that applies to.
-template <int NG, bool VALUED, bool MAXR = false, bool FUSE = false>
+// W = floats per lane: 4 (16-byte slices: K % 4 == 0, aligned operands) or 1 (4-byte slices: ANY K <= 32 / NG and any
+// 4-byte alignment -- the class-count widths of a GCN's last layer, K = 3, 7, ...; cp.async.ca, the only 4-byte form).
+template <int NG, bool VALUED, bool MAXR = false, bool FUSE = false, int W = 4>
 struct WalkerSub {
-    using P = Pack<true>;
-    using T = float4;
+    using P = Pack<W == 4>;
+    using T = typename P::T;
+    static_assert(W == 4 || W == 1, "16-byte or 4-byte slices");
     using R = Reduce<P, VALUED, MAXR, FUSE>;
     using E = Epilogue<P, FUSE>;
     static constexpr bool kFuse = FUSE;
@@ -675,9 +694,10 @@ struct WalkerSub {
     static constexpr int SN = QS * NG;              // nonzeros per stage
     static constexpr int SPC = Q / QS;              // stages per chunk (1 or 2)
     static constexpr int UB = 4;                    // quads read back from the ring per LDS batch
-    static constexpr int kStageBytes = QS * 512;
+    static constexpr int kRowBytes = 32 * 4 * W;    // one warp-wide copy (NG B rows) in the ring
+    static constexpr int kStageBytes = QS * kRowBytes;
     static constexpr int kRingBytes = 2 * kStageBytes;  // per warp: one stage in flight, one being consumed
-    static constexpr int kPanel = LPR * 4;          // columns one warp covers (>= K: a single panel)
+    static constexpr int kPanel = LPR * W;          // columns one warp covers (>= K: a single panel)
     static_assert(QS % UB == 0 && Q % QS == 0, "bad stage shape");
 
     float init_v;
@@ -701,11 +721,11 @@ struct WalkerSub {
 
     __device__ __forceinline__ void init(const Operands &o, int /*panel*/, int K, int ln, unsigned ring_base) {
         lane = ln; g = ln / LPR;
-        const int col0 = (ln % LPR) * 4;
+        const int col0 = (ln % LPR) * W;
         active = col0 < K;
         colind = o.colind; val = o.val; Bl = reinterpret_cast<const char *>(o.B + col0); Cl = o.C + col0;
         ldb_bytes = (unsigned)o.ldb * 4u; ldc = o.ldc;
-        ring = ring_base + ln * 16;
+        ring = ring_base + ln * (4 * W);
         init_v = o.init;
         if constexpr (FUSE) {
             col_scale = o.col_scale; row_scale = o.row_scale; my_rs = 1.f;
@@ -732,8 +752,12 @@ struct WalkerSub {
 #pragma unroll
         for (int off = 16; off >= LPR; off >>= 1) {
             T x;
-            x.x = __shfl_xor_sync(kFull, t.x, off); x.y = __shfl_xor_sync(kFull, t.y, off);
-            x.z = __shfl_xor_sync(kFull, t.z, off); x.w = __shfl_xor_sync(kFull, t.w, off);
+            if constexpr (W == 4) {
+                x.x = __shfl_xor_sync(kFull, t.x, off); x.y = __shfl_xor_sync(kFull, t.y, off);
+                x.z = __shfl_xor_sync(kFull, t.z, off); x.w = __shfl_xor_sync(kFull, t.w, off);
+            } else {
+                x = __shfl_xor_sync(kFull, t, off);
+            }
             R::merge(t, x);
         }
     }
@@ -765,7 +789,10 @@ struct WalkerSub {
             }
 #pragma unroll
             for (int i = 0; i < UB; i++)
-                if (active && (FULL || pos0 + (i0 + i) * NG + g < n)) cp_async16<0>(ring + slot + (i0 + i) * 512, bp[i]);
+                if (active && (FULL || pos0 + (i0 + i) * NG + g < n)) {
+                    if constexpr (W == 4) cp_async16<0>(ring + slot + (i0 + i) * kRowBytes, bp[i]);
+                    else cp_async4(ring + slot + (i0 + i) * kRowBytes, bp[i]);
+                }
         }
         cp_async_commit();
     }
@@ -788,7 +815,8 @@ struct WalkerSub {
                 // beyond K) holds stale ring bytes that are never added to anything that is stored
                 a[i] = VALUED ? __shfl_sync(kFull, vals, pos0 + (i0 + i) * NG + g) : 1.f;
                 sc[i] = FUSE ? __shfl_sync(kFull, scales, pos0 + (i0 + i) * NG + g) : 1.f;
-                b[i] = lds128(ring + slot + (i0 + i) * 512);
+                if constexpr (W == 4) b[i] = lds128(ring + slot + (i0 + i) * kRowBytes);
+                else b[i] = lds32(ring + slot + (i0 + i) * kRowBytes);
             }
             if (FULL && ((endmask >> (pos0 + i0 * NG)) & low_bits(UB * NG)) == 0u) {  // no row ends in these UB quads
 #pragma unroll
@@ -1124,6 +1152,165 @@ spmm_flat_kernel(int M, int K, long long total_keys, int task, int long_row, con
 }
 
 // =================================================================================================
+// Kernel A for tiny B rows that are not 16-byte multiples (K <= 16 with K % 4 != 0, or unaligned operands)
+// =================================================================================================
+// The class-count widths of a GCN's last layer (K = 3, 7, ...).  A B row is then 12-60 bytes at a 4-byte aligned
+// address: no 16-byte cp.async, and one row per warp instruction would keep 3-15 of 32 lanes busy.  Here a warp is
+// NG = 32 / LPR lane groups (LPR = 4 / 8 / 16 lanes >= K), lane `sl` of a group owns column `sl`, and every group sums
+// its OWN row: nonzeros in CSR order into one accumulator per element -- the reference's order, bit-identical -- LPR
+// nonzeros per step (the group's lanes hold the next LPR column indices, the following LPR are prefetched), each
+// lane issuing up to 8 independent 4-byte gathers before the first add.  Rows are dealt dynamically: the lanes hold
+// the row bounds of a 32-row batch, and a group that finishes its row takes the next unassigned row of the batch
+// (ranked by ballot among the groups finishing in the same step), so a long row delays only its own group and the next
+// batch is fetched as soon as the current one has been handed out.  No shared memory; B this narrow lives in the L2.
+// Same task windows as spmm_flat_kernel (one task per warp); rows above `long_row` are left to kernel B.
+constexpr int kRgWarps = 4;        // warps (= tasks) per CTA
+constexpr int kRowGroupMaxK = 16;  // widest B row the row-group kernel takes
+
+template <int LPR, bool VALUED, bool MAXR, bool FUSE>
+__global__ void __launch_bounds__(kRgWarps * 32)
+spmm_rowgroup_kernel(int M, int K, long long total_keys, int task, int long_row, const int *__restrict__ rowptr, Operands op)
+{
+    using P = Pack<false>;
+    using R = Reduce<P, VALUED, MAXR, FUSE>;
+    using E = Epilogue<P, FUSE>;
+    static_assert(LPR == 4 || LPR == 8 || LPR == 16, "4, 8 or 16 lanes per row");
+    constexpr int NG = 32 / LPR;
+    constexpr int UB = LPR < 8 ? LPR : 8;  // gathers in flight per lane
+    constexpr unsigned kLeaders = LPR == 4 ? 0x11111111u : (LPR == 8 ? 0x01010101u : 0x00010001u);  // lane 0 of every group
+
+    const int lane = threadIdx.x & 31;
+    const int g = lane / LPR, sl = lane % LPR, lead = g * LPR;
+    const bool active = sl < K;
+    const long long k0 = ((long long)blockIdx.x * kRgWarps + (threadIdx.x >> 5)) * task;
+    if (k0 >= total_keys) return;  // whole warps leave; the kernel has no CTA-wide synchronisation
+
+    int row_lo, row_hi;
+    {
+        const int shift = lane & 16;
+        const long long target = k0 + (shift ? task : 0);
+        const int r = search_key16(rowptr, M, target < total_keys ? target : total_keys + 1, lane & 15, shift);
+        row_lo = __shfl_sync(kFull, r, 0);
+        row_hi = __shfl_sync(kFull, r, 16);
+    }
+
+    const int *__restrict__ colind = op.colind;
+    const float *__restrict__ val = op.val;
+    const float *__restrict__ Bl = op.B + sl;
+    float *__restrict__ Cl = op.C + sl;
+    const int ldb = op.ldb, ldc = op.ldc;
+    const float init_v = op.init;
+    [[maybe_unused]] const bool has_bias = FUSE && op.bias != nullptr;
+    [[maybe_unused]] const float bias = (has_bias && active) ? __ldg(op.bias + sl) : 0.f;
+    const unsigned below = kLeaders & ((1u << lead) - 1u);  // the leaders of the groups before mine
+
+    // the batch of 32 rows being handed out: lane i holds the bounds (and scale) of row rb + i
+    int rb = row_lo, next_rb = row_lo;
+    unsigned rows_left = 0;  // rows of the batch (bits = row - rb) that wait for a group: non-empty, not long
+    int my_start = 0, my_end = 0;
+    [[maybe_unused]] float my_rs = 1.f;
+    // my group's row
+    int row = -1, p = 0, e = 0;
+    int ccol = 0, ncol = 0;
+    float cval = 1.f, nval = 1.f;
+    [[maybe_unused]] float csc = 1.f, rs = 1.f;
+    float acc = R::start(init_v);
+
+    while (true) {
+        const bool need = row < 0;
+        const unsigned needm = __ballot_sync(kFull, need) & kLeaders;
+        // ---- next batch, as soon as some group is idle and the current batch has been handed out --------------
+        while (needm != 0u && rows_left == 0u && next_rb < row_hi) {
+            rb = next_rb;
+            next_rb += 32;
+            const int nrows = min(32, row_hi - rb);
+            my_start = my_end = 0;
+            if (lane < nrows) {
+                my_start = __ldg(rowptr + rb + lane);
+                my_end = __ldg(rowptr + rb + lane + 1);
+            }
+            if constexpr (FUSE) my_rs = (op.row_scale && lane < nrows) ? __ldg(op.row_scale + rb + lane) : 1.f;
+            const int len = my_end - my_start;
+            const unsigned longm = __ballot_sync(kFull, len > long_row);  // left to kernel B
+            rows_left = __ballot_sync(kFull, len > 0) & ~longm;
+            unsigned em = ~(rows_left | longm) & low_bits(nrows);
+            while (em) {  // empty rows: the reduction's start value, NG rows per store instruction
+                const unsigned bit = __fns(em, 0, g + 1);
+                [[maybe_unused]] float rsv = 1.f;
+                if constexpr (FUSE) rsv = __shfl_sync(kFull, my_rs, bit & 31u);
+                if (bit != 0xffffffffu && active)
+                    __stcs(Cl + (long long)(rb + (int)bit) * ldc, E::apply(R::start(init_v), rsv, bias, has_bias));
+#pragma unroll
+                for (int i = 0; i < NG; i++) em &= em - 1;  // (0 & -1 stays 0)
+            }
+        }
+        // ---- idle groups take the next rows of the batch, in group order ----------------------------------------
+        if (needm != 0u && rows_left != 0u) {
+            const unsigned bit = need ? __fns(rows_left, 0, __popc(needm & below) + 1) : 0xffffffffu;
+            const bool got = bit != 0xffffffffu;
+            const int src = got ? (int)bit : 0;
+            const int ns = __shfl_sync(kFull, my_start, src), ne = __shfl_sync(kFull, my_end, src);
+            [[maybe_unused]] float nrs = 1.f;
+            if constexpr (FUSE) nrs = __shfl_sync(kFull, my_rs, src);
+            if (got) {
+                row = rb + src; p = ns; e = ne;
+                acc = R::start(init_v);
+                if constexpr (FUSE) rs = nrs;
+                ccol = ncol = 0;
+                if (p + sl < e) {
+                    ccol = __ldcs(colind + p + sl);
+                    if (VALUED) cval = __ldcs(val + p + sl);
+                }
+                if (p + LPR + sl < e) {
+                    ncol = __ldcs(colind + p + LPR + sl);
+                    if (VALUED) nval = __ldcs(val + p + LPR + sl);
+                }
+                if constexpr (FUSE) csc = (op.col_scale && p + sl < e) ? __ldg(op.col_scale + ccol) : 1.f;
+            }
+            const int taken = min(__popc(needm), __popc(rows_left));
+            for (int i = 0; i < taken; i++) rows_left &= rows_left - 1;
+        }
+        if (__ballot_sync(kFull, row >= 0) == 0u) {
+            if (rows_left == 0u && next_rb >= row_hi) break;  // every row of the task is done
+            continue;                                          // (a batch of empty / long rows only)
+        }
+        // ---- one step: up to LPR nonzeros of my group's row -------------------------------------------------------
+        const int n = row >= 0 ? min(LPR, e - p) : 0;
+#pragma unroll
+        for (int u0 = 0; u0 < LPR; u0 += UB) {
+            float b[UB], a[UB];
+            [[maybe_unused]] float sc[UB];
+#pragma unroll
+            for (int u = 0; u < UB; u++) {
+                const int c = __shfl_sync(kFull, ccol, lead + u0 + u);
+                a[u] = VALUED ? __shfl_sync(kFull, cval, lead + u0 + u) : 1.f;
+                if constexpr (FUSE) sc[u] = __shfl_sync(kFull, csc, lead + u0 + u);
+                b[u] = 0.f;
+                if (u0 + u < n && active) b[u] = __ldg(Bl + (long long)c * ldb);
+            }
+#pragma unroll
+            for (int u = 0; u < UB; u++)
+                if (u0 + u < n) R::step(acc, a[u], b[u], FUSE ? sc[u] : 1.f);
+        }
+        p += n;
+        if (row >= 0) {
+            if (p >= e) {  // the row is complete
+                if (active) __stcs(Cl + (long long)row * ldc, E::apply(acc, rs, bias, has_bias));
+                row = -1;
+            } else {       // the prefetched indices become current; fetch the ones after them
+                ccol = ncol; cval = nval;
+                if constexpr (FUSE) csc = (op.col_scale && p + sl < e) ? __ldg(op.col_scale + ccol) : 1.f;
+                ncol = 0;
+                if (p + LPR + sl < e) {
+                    ncol = __ldcs(colind + p + LPR + sl);
+                    if (VALUED) nval = __ldcs(val + p + LPR + sl);
+                }
+            }
+        }
+    }
+}
+
+// =================================================================================================
 // Kernel B: long rows.  8 warps per CTA, clusters of 8 CTAs.  Claim by probing, then segmented
 // cooperative sums: one CTA per long row, the whole cluster (64 warps, partials combined through
 // distributed shared memory) per huge row.
@@ -1317,31 +1504,41 @@ cudaError_t allow_smem(KernelT kern, int bytes, std::atomic<bool> (&done)[kMaxDe
     return cudaSuccess;
 }
 
+// Kernel B (when some row may be long), forked onto the helper stream; *sd_out is the helper to join afterwards.
+template <class WKB, int V, bool VEC4>
+cudaError_t launch_long(const Args &a, unsigned panels, Side **sd_out)
+{
+    *sd_out = nullptr;
+    if (!a.has_long) return cudaSuccess;
+    Side *sd = a.overlap ? side_for_current_device() : nullptr;
+    constexpr int dynB = WKB::kRingBytes * kLongWarps;
+    auto kernB = spmm_long_kernel<WKB, V, VEC4>;
+    if (dynB > 0) {  // static + dynamic shared memory exceeds the 48 KB default
+        static std::atomic<bool> done[kMaxDevices];
+        const cudaError_t e = allow_smem(kernB, dynB, done);
+        if (e != cudaSuccess) return e;
+    }
+    cudaStream_t sb = a.st;
+    if (sd) {
+        if (cudaEventRecord(sd->fork, a.st) != cudaSuccess || cudaStreamWaitEvent(sd->stream, sd->fork, 0) != cudaSuccess)
+            return cudaGetLastError();
+        sb = sd->stream;
+    }
+    const unsigned ctas = (unsigned)((a.nnz + kProbeWindow - 1) / kProbeWindow);
+    dim3 grid((ctas + kClusterSize - 1) / kClusterSize * kClusterSize, panels, 1);  // whole clusters
+    kernB<<<grid, kLongWarps * 32, dynB, sb>>>(a.M, a.K, (int)a.nnz, a.long_row, a.rowptr, a.op);
+    if (sd && cudaEventRecord(sd->join, sd->stream) != cudaSuccess) return cudaGetLastError();
+    *sd_out = sd;
+    return cudaGetLastError();
+}
+
 template <class WK, int V, bool VEC4, int MINB, class WKB = WK>
 cudaError_t launch(const Args &a)
 {
     const unsigned panels = (unsigned)((a.K + WK::kPanel - 1) / WK::kPanel);
-    const bool has_b = a.has_long;
-    Side *sd = (has_b && a.overlap) ? side_for_current_device() : nullptr;
-    if (has_b) {
-        constexpr int dynB = WKB::kRingBytes * kLongWarps;
-        auto kernB = spmm_long_kernel<WKB, V, VEC4>;
-        if (dynB > 0) {  // static + dynamic shared memory exceeds the 48 KB default
-            static std::atomic<bool> done[kMaxDevices];
-            const cudaError_t e = allow_smem(kernB, dynB, done);
-            if (e != cudaSuccess) return e;
-        }
-        cudaStream_t sb = a.st;
-        if (sd) {
-            if (cudaEventRecord(sd->fork, a.st) != cudaSuccess || cudaStreamWaitEvent(sd->stream, sd->fork, 0) != cudaSuccess)
-                return cudaGetLastError();
-            sb = sd->stream;
-        }
-        const unsigned ctas = (unsigned)((a.nnz + kProbeWindow - 1) / kProbeWindow);
-        dim3 grid((ctas + kClusterSize - 1) / kClusterSize * kClusterSize, panels, 1);  // whole clusters
-        kernB<<<grid, kLongWarps * 32, dynB, sb>>>(a.M, a.K, (int)a.nnz, a.long_row, a.rowptr, a.op);
-        if (sd && cudaEventRecord(sd->join, sd->stream) != cudaSuccess) return cudaGetLastError();
-    }
+    Side *sd = nullptr;
+    const cudaError_t eb = launch_long<WKB, V, VEC4>(a, panels, &sd);
+    if (eb != cudaSuccess) return eb;
     constexpr int dynA = WK::kRingBytes;
     auto kernA = spmm_flat_kernel<WK, V, VEC4, MINB>;
     const long long total = a.nnz + a.M;
@@ -1352,6 +1549,28 @@ cudaError_t launch(const Args &a)
     kernA<<<grid, 32, dynA + pad, a.st>>>(a.M, a.K, total, a.task, a.long_row, a.rowptr, a.op);
     if (sd && cudaStreamWaitEvent(a.st, sd->join, 0) != cudaSuccess) return cudaGetLastError();
     return cudaGetLastError();
+}
+
+// Tiny B rows that are not 16-byte multiples: spmm_rowgroup_kernel, long rows through the scalar register walker.
+template <int LPR, bool VALUED, bool MAXR, bool FUSE>
+cudaError_t launch_rowgroup(const Args &a)
+{
+    Side *sd = nullptr;
+    const cudaError_t eb = launch_long<Walker<1, VALUED, false, 8, MAXR, FUSE>, 1, false>(a, 1u, &sd);
+    if (eb != cudaSuccess) return eb;
+    const long long total = a.nnz + a.M;
+    const long long ntask = (total + a.task - 1) / a.task;
+    const unsigned blocks = (unsigned)((ntask + kRgWarps - 1) / kRgWarps);
+    spmm_rowgroup_kernel<LPR, VALUED, MAXR, FUSE><<<blocks, kRgWarps * 32, 0, a.st>>>(a.M, a.K, total, a.task, a.long_row, a.rowptr, a.op);
+    if (sd && cudaStreamWaitEvent(a.st, sd->join, 0) != cudaSuccess) return cudaGetLastError();
+    return cudaGetLastError();
+}
+template <bool VALUED, bool MAXR, bool FUSE>
+cudaError_t dispatch_rowgroup(int K, const Args &a)
+{
+    if (K <= 4) return launch_rowgroup<4, VALUED, MAXR, FUSE>(a);
+    if (K <= 8) return launch_rowgroup<8, VALUED, MAXR, FUSE>(a);
+    return launch_rowgroup<16, VALUED, MAXR, FUSE>(a);
 }
 
 template <int V, bool VALUED, bool VEC4, int U, int MINB, bool MAXR = false, bool FUSE = false>
@@ -1481,6 +1700,16 @@ cudaError_t dispatch_sub(int K, const Args &a)
     return launch<WalkerSub<8, VALUED, MAXR, FUSE>, 1, true, 24>(a);
 }
 
+// Narrow B that is not made of 16-byte slices (any K <= 16, any 4-byte alignment): the same walker on 4-byte slices,
+// NG = 2 / 4 / 8 nonzeros per warp-wide copy for K <= 16 / 8 / 4.
+template <bool VALUED, bool MAXR, bool FUSE>
+cudaError_t dispatch_sub1(int K, const Args &a)
+{
+    if (K > 8) return launch<WalkerSub<2, VALUED, MAXR, FUSE, 1>, 1, false, 24>(a);
+    if (K > 4) return launch<WalkerSub<4, VALUED, MAXR, FUSE, 1>, 1, false, 24>(a);
+    return launch<WalkerSub<8, VALUED, MAXR, FUSE, 1>, 1, false, 24>(a);
+}
+
 // The row-parallel narrow walker (sequential order); long rows go to kernel B with the sub-warp walker.
 template <bool VALUED, bool MAXR, bool FUSE>
 cudaError_t dispatch_rows(int K, const Args &a)
@@ -1518,6 +1747,19 @@ cudaError_t dispatch_reg4(int V, const Args &a)
 template <bool VALUED>
 cudaError_t dispatch_all(int mode, bool vec4, bool peer, int walker, bool hint, int V, bool masked, int K, const Args &a)
 {
+    if (!vec4 && K <= kRowGroupMaxK && walker != GESPMM_WALKER_REGISTER) {
+        // tiny rows of any width: lane groups on 4-byte slices.  Sequential order (GESPMM_WALKER_ROWS /
+        // GESPMM_FLAG_SEQUENTIAL, and max, where the order is free): every group sums its own row (row-group kernel);
+        // default: the groups share a row's nonzeros (sub-warp walker, re-associated like its 16-byte form).
+        if (walker == GESPMM_WALKER_ROWS || walker == GESPMM_WALKER_RING) {
+            if (mode == 1) return dispatch_rowgroup<VALUED, true, false>(K, a);
+            if (mode == 2) return dispatch_rowgroup<VALUED, false, true>(K, a);
+            return dispatch_rowgroup<VALUED, false, false>(K, a);
+        }
+        if (mode == 1) return dispatch_sub1<VALUED, true, false>(K, a);
+        if (mode == 2) return dispatch_sub1<VALUED, false, true>(K, a);
+        return dispatch_sub1<VALUED, false, false>(K, a);
+    }
     if (!vec4) {
         if (mode == 1) return dispatch_scalar<VALUED, true, false>(V, a);
         if (mode == 2) return dispatch_scalar<VALUED, false, true>(V, a);
@@ -1620,6 +1862,8 @@ int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr
     // the sub-warp walker spends 1/NG of the instructions per nonzero, so a task's start-up weighs NG times more:
     // measured optima are 512 (cit-Patents shape) to 1024 (ogbn-products, R-MAT, Reddit shapes) at K = 16, 32
     if (sub || rows_walker) tk *= (K > 32 ? 2 : (K > 16 ? 4 : 8));
+    const bool rowgroup = !vec4 && K <= kRowGroupMaxK && ch.walker != GESPMM_WALKER_REGISTER;
+    if (rowgroup) tk *= (K > 8 ? 2 : (K > 4 ? 4 : 8));  // NG rows at a time: a task's start-up weighs NG times more
     const long long cap = (total / (8 * warps_per_wave)) & ~31LL;
     if (tk > cap) tk = cap;
     int task = (int)(tk < 32 ? 32 : (tk > kMaxTask ? kMaxTask : tk));
@@ -1646,6 +1890,10 @@ int sequential_for(int64_t K, int64_t row_nnz, const Choice &ch)
 {
     if (row_nnz > ch.long_row) return 0;  // segmented (kernel B)
     if (row_nnz > 1 && use_subwarp(K, ch.walker) && !use_rows(K, ch.walker)) return 0;  // per-group partial sums
+    // widths that are not multiples of 4 up to 16: the same sub-warp walker on 4-byte slices unless a sequential
+    // walker was asked for (row-group kernel / register walker)
+    if (row_nnz > 1 && K % 4 != 0 && K <= kRowGroupMaxK &&
+        (ch.walker == GESPMM_WALKER_AUTO || ch.walker == GESPMM_WALKER_SUBWARP)) return 0;
     return 1;
 }
 

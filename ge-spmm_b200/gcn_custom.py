@@ -4,20 +4,20 @@ reference ships as pytorch-custom/gcn_custom.py (2 layers) and gcn_custom_2layer
 Same model (GCNConv -> relu -> dropout -> GCNConv -> log_softmax), optimiser (Adam, lr 0.01, weight
 decay 5e-4 on the first layer), 200 epochs under torch.autograd.profiler and the same per-epoch log
 line.  Planetoid cannot be downloaded here, so:
-  * the graph is the real PubMed adjacency the reference bundles as data/misc/pubmed.mtx
-    (tests/golden/pubmed_csr.npz, parsed by the reference's own reader) plus self-loops
-    (gcn_custom.py:33-34);
+  * the graph is read from a MatrixMarket file with the library's reader (``--mtx``; e.g. the PubMed
+    adjacency the reference bundles as data/misc/pubmed.mtx) or, without one, is a seeded
+    PubMed-shaped synthetic graph (19,717 nodes, 88,648 directed edges, symmetric); self-loops are
+    added either way (gcn_custom.py:33-34);
   * features (500 columns, row-normalised like T.NormalizeFeatures) and the 3 class labels are
     synthetic: labels come from a planted 2-hop linear teacher, so there is something to learn;
   * the CSC arrays come from spmm.csr2csc on the GPU instead of scipy's tocsc() (gcn_custom.py:39-46).
 
-    python ge-spmm_b200/gcn_custom.py --n-hidden 64 [--layers 3] [--epochs 200] [--fuse-norm] [--profile]
+    python ge-spmm_b200/gcn_custom.py --n-hidden 64 [--layers 3] [--epochs 200] [--fuse-norm] [--profile] [--mtx FILE]
 """
 import argparse
 import os
 import sys
 
-import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -27,11 +27,14 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
 
-def load_problem(device, n_features=500, n_classes=3, seed=0):
-    from gespmm_b200 import graphs
+def load_problem(device, n_features=500, n_classes=3, seed=0, mtx=None):
+    from gespmm_b200 import capi, graphs
     from gespmm_b200.op import spmm
-    z = np.load(os.path.join(ROOT, "tests", "golden", "pubmed_csr.npz"))
-    rowptr, colind = torch.from_numpy(z["rowptr"]), torch.from_numpy(z["colind"])
+    if mtx is not None:
+        _, _, rp, ci, _ = capi.read_mtx(mtx)
+        rowptr, colind = torch.from_numpy(rp), torch.from_numpy(ci)
+    else:
+        rowptr, colind = graphs.social_like(19717, 88648, seed=seed + 11, sigma=1.0, locality=0.3, window=0.01)
     n = rowptr.numel() - 1
     rows = torch.repeat_interleave(torch.arange(n), (rowptr[1:] - rowptr[:-1]).long())
     loop = torch.arange(n)
@@ -71,10 +74,10 @@ class Net(torch.nn.Module):
         return F.log_softmax(self.convs[-1](x, *a), dim=1)
 
 
-def run(n_hidden=64, layers=2, epochs=200, fuse_norm=False, profile=False, device="cuda", log=print):
+def run(n_hidden=64, layers=2, epochs=200, fuse_norm=False, profile=False, device="cuda", log=print, mtx=None):
     entry.load_package()
     device = torch.device(device)
-    g, x, y, masks, n_in, n_out = load_problem(device)
+    g, x, y, masks, n_in, n_out = load_problem(device, mtx=mtx)
     torch.manual_seed(0)
     model = Net(n_in, n_hidden, n_out, layers, fuse_norm).to(device)
     opt = torch.optim.Adam([dict(params=model.reg_params, weight_decay=5e-4),
@@ -118,5 +121,6 @@ if __name__ == "__main__":
     ap.add_argument("--epochs", type=int, default=200)
     ap.add_argument("--fuse-norm", action="store_true")
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--mtx", default=None, help="MatrixMarket adjacency (default: a PubMed-shaped synthetic graph)")
     a = ap.parse_args()
-    print(run(a.n_hidden, a.layers, a.epochs, a.fuse_norm, a.profile))
+    print(run(a.n_hidden, a.layers, a.epochs, a.fuse_norm, a.profile, mtx=a.mtx))

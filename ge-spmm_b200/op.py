@@ -13,12 +13,20 @@ Differences, all deliberate:
   * forward does not stash ``feat`` in ctx (op.py:16 keeps [N,K] alive for nothing);
   * ``normalize=False`` works (op.py:131-134 calls ``rowptr.shape(0)``, a TypeError);
   * the "[I] Treat edge weight as no_grad." notice (op.py:31) is printed once, not per call;
-  * ``GCNConv(..., fuse_norm=True)`` (new, off by default) folds the two degree-normalisation
-    passes around the aggregation (op.py:142,145: ``x * out_deg_norm`` before, ``* in_deg_norm``
-    after, 2 x N x K x 4 bytes each way) into the edge values of the valued kernel:
-    w[p] = in_norm[row(p)] * ew[p] * out_norm[col(p)], computed once and cached.
+  * ``GCNConv(..., fuse_norm=True)`` (new, off by default) runs the two degree-normalisation
+    passes around the aggregation and the bias add (op.py:142-147: ``x * out_deg_norm`` before,
+    ``* in_deg_norm`` and ``+ bias`` after -- three extra passes over [N, K]) INSIDE the kernel:
+    the gathered row of x is scaled by its column's out_deg_norm, the finished row by in_deg_norm
+    and offset by the bias on its way out (gespmm_opts.row_scale / col_scale / bias), each a
+    separately rounded fp32 operation in the unfused order, so the fused layer's output is
+    bit-identical to the unfused one's; the unvalued kernel stays unvalued (no per-edge weights);
+  * the summation order is a per-call choice (``set_sequential``), not an environment variable:
+    by default K <= 64 uses the faster re-associating walker (within ~2e-6 of max|out| of the
+    reference's order, deterministic); ``set_sequential(True)`` makes every row of at most 4096
+    nonzeros bit-identical to the reference kernels at every K.
 """
 import importlib
+import importlib.util
 import math
 import os
 import sys
@@ -43,6 +51,22 @@ def _load_spmm():
 spmm = _load_spmm()
 
 _warned_no_grad = False
+_sequential = False
+
+
+def set_sequential(on=True):
+    """Per-process default of this module's calls for GESPMM_FLAG_SEQUENTIAL (see include/gespmm.h): sum every row of
+    at most 4096 nonzeros in the reference's strictly sequential CSR order, for every K.  Returns the old value."""
+    global _sequential
+    old, _sequential = _sequential, bool(on)
+    return old
+
+
+def _product(rowptr, colind, val, feat, row_scale=None, col_scale=None, bias=None):
+    if _sequential or row_scale is not None or col_scale is not None or bias is not None:
+        return spmm.csr_spmm_ex(rowptr, colind, val, feat, sequential=_sequential, row_scale=row_scale,
+                                col_scale=col_scale, bias=bias)
+    return spmm.csr_spmm_no_edge_value(rowptr, colind, feat) if val is None else spmm.csr_spmm(rowptr, colind, val, feat)
 
 
 class SPMMFunction(torch.autograd.Function):
@@ -50,10 +74,7 @@ class SPMMFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, rowptr, colind, colptr, rowind, feat, edge_weight_csr=None, edge_weight_csc=None):
-        if edge_weight_csr is None:
-            out = spmm.csr_spmm_no_edge_value(rowptr, colind, feat)
-        else:
-            out = spmm.csr_spmm(rowptr, colind, edge_weight_csr, feat)
+        out = _product(rowptr, colind, edge_weight_csr, feat)
         ctx.backward_csc = (colptr, rowind, edge_weight_csr, edge_weight_csc)
         return out
 
@@ -68,13 +89,40 @@ class SPMMFunction(torch.autograd.Function):
                     "Backward of SPMM require edge values in both src-first and dst-first order, "
                     "and do not support gradients for edge values. Call with SPMMFunction.apply(rowptr, colind, "
                     "colptr, rowind, in_feat, edge_value_row_first, edge_value_col_first")
-            grad_feat = spmm.csr_spmm(colptr, rowind, edge_weight_csc, grad_out)
+            grad_feat = _product(colptr, rowind, edge_weight_csc, grad_out)
             if not _warned_no_grad:
                 print("[I] Treat edge weight as no_grad.")
                 _warned_no_grad = True
         else:
-            grad_feat = spmm.csr_spmm_no_edge_value(colptr, rowind, grad_out)
+            grad_feat = _product(colptr, rowind, None, grad_out)
         return None, None, None, None, grad_feat, None, None
+
+
+class FusedSPMMFunction(torch.autograd.Function):
+    """out = (A @ (feat * col_scale)) * row_scale + bias in ONE kernel (gespmm_opts.row_scale / col_scale / bias), i.e.
+    GCNConv's ``x * out_deg_norm`` -> SPMMFunction -> ``* in_deg_norm`` -> ``+ bias`` (op.py:142-147) without the three
+    element-wise passes; bit-identical to them.  Backward: grad_feat = (A^T @ (grad_out * row_scale)) * col_scale, the
+    same fused kernel on the CSC arrays with the two scales swapped; grad_bias = column sums of grad_out.  The scales
+    (functions of the graph) and the edge weights get no gradient, like the reference's edge weights."""
+
+    @staticmethod
+    def forward(ctx, rowptr, colind, colptr, rowind, feat, row_scale, col_scale, bias=None, edge_weight_csr=None,
+                edge_weight_csc=None):
+        if edge_weight_csr is not None and edge_weight_csc is None:
+            raise RuntimeError("edge values are needed in both src-first and dst-first order (see SPMMFunction)")
+        rs = None if row_scale is None else row_scale.reshape(-1).contiguous()
+        cs = None if col_scale is None else col_scale.reshape(-1).contiguous()
+        out = _product(rowptr, colind, edge_weight_csr, feat, rs, cs, None if bias is None else bias.detach().contiguous())
+        ctx.backward_csc = (colptr, rowind, edge_weight_csc, rs, cs, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        colptr, rowind, edge_weight_csc, rs, cs, has_bias = ctx.backward_csc
+        grad_out = grad_out.contiguous()
+        grad_feat = _product(colptr, rowind, edge_weight_csc, grad_out, cs, rs, None) if ctx.needs_input_grad[4] else None
+        grad_bias = grad_out.sum(dim=0) if (has_bias and ctx.needs_input_grad[7]) else None
+        return None, None, None, None, grad_feat, None, None, grad_bias, None, None
 
 
 def glorot(tensor):
@@ -87,14 +135,6 @@ def glorot(tensor):
 def zeros(tensor):
     if tensor is not None:
         tensor.data.fill_(0)
-
-
-def _fused_edge_weights(indptr, indices, row_norm, col_norm, ew):
-    """w[p] = row_norm[row(p)] * ew[p] * col_norm[indices[p]] for a CSR given by (indptr, indices)."""
-    deg = (indptr[1:] - indptr[:-1]).long()
-    rows = torch.repeat_interleave(torch.arange(deg.numel(), device=indptr.device), deg)
-    w = row_norm.reshape(-1)[rows] * col_norm.reshape(-1)[indices.long()]
-    return (w if ew is None else w * ew).contiguous()
 
 
 class GCNConv(torch.nn.Module):
@@ -121,7 +161,6 @@ class GCNConv(torch.nn.Module):
         zeros(self.bias)
         self.cached_result = None
         self.cached_num_edges = None
-        self.cached_fused = None
 
     @staticmethod
     def in_deg_sqrt(indptr):
@@ -143,12 +182,9 @@ class GCNConv(torch.nn.Module):
             self.cached_result = in_deg_norm, out_deg_norm
         in_deg_norm, out_deg_norm = self.cached_result
         if self.normalize and self.fuse_norm:
-            if not self.cached or self.cached_fused is None:
-                self.cached_fused = (_fused_edge_weights(rowptr, colind, in_deg_norm, out_deg_norm, edge_weight_csr),
-                                     _fused_edge_weights(colptr, rowind, out_deg_norm, in_deg_norm, edge_weight_csc))
-            w_csr, w_csc = self.cached_fused
-            aggr_out = SPMMFunction.apply(rowptr, colind, colptr, rowind, x, w_csr, w_csc)
-            return aggr_out if self.bias is None else aggr_out + self.bias
+            # one kernel: gathered rows scaled by out_deg_norm, finished rows by in_deg_norm, bias added on the way out
+            return FusedSPMMFunction.apply(rowptr, colind, colptr, rowind, x, in_deg_norm, out_deg_norm, self.bias,
+                                           edge_weight_csr, edge_weight_csc)
         if self.normalize:
             x = x * out_deg_norm
         aggr_out = SPMMFunction.apply(rowptr, colind, colptr, rowind, x, edge_weight_csr, edge_weight_csc)

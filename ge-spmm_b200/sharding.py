@@ -43,8 +43,10 @@ def shard_csr(rowptr, colind, val, lo, hi):
     return rp, ci, v
 
 
-def _cuda_spmm(rowptr, colind, val, B):
+def _cuda_spmm(rowptr, colind, val, B, max_row_nnz=-1):
     from .op import spmm  # fails loudly if the extension is missing; rejects CPU tensors
+    if max_row_nnz >= 0:  # a per-graph figure: lets the call skip the long-row kernel when no row is long
+        return spmm.csr_spmm_ex(rowptr, colind, val, B, max_row_nnz=max_row_nnz)
     return spmm.csr_spmm_no_edge_value(rowptr, colind, B) if val is None else spmm.csr_spmm(rowptr, colind, val, B)
 
 
@@ -69,7 +71,33 @@ class RowShardedSpMM:
         self.rowptr, self.colind = rp.to(self.device), ci.to(self.device)
         self.val = None if v is None else v.to(self.device)
         self.nnz_local = int(self.colind.numel())
-        self.spmm_fn = spmm_fn or _cuda_spmm
+        self.spmm_fn = spmm_fn
+        # the longest row of this rank's block, once per graph (gespmm_max_row_nnz): products over a block without
+        # long rows launch one kernel instead of two
+        self.max_row_nnz = -1
+        if spmm_fn is None and self.rowptr.is_cuda:
+            from .op import spmm
+            self.max_row_nnz = int(spmm.max_row_nnz(self.rowptr))
+
+    def even_b_block(self):
+        """Rows per rank when B is row-sharded in equal blocks (the last one may be short): ceil(N / world)."""
+        return -(-self.N // self.world)
+
+    def all_gather_B_even(self, B_block, out=None):
+        """B row-sharded in EQUAL blocks of even_b_block() rows (rank p holds rows [p*blk, (p+1)*blk), zero-padded past
+        N): ONE all_gather_into_tensor assembles all of B on every rank; returns the [N, K] view of the padded buffer."""
+        blk, K = self.even_b_block(), B_block.shape[1]
+        assert B_block.shape[0] == blk and B_block.is_contiguous()
+        full = out if out is not None else torch.empty(blk * self.world, K, dtype=B_block.dtype, device=B_block.device)
+        if self.world == 1:
+            full[:blk].copy_(B_block)
+        else:
+            dist.all_gather_into_tensor(full, B_block, group=self.group)
+        return full[:self.N]
+
+    def distinct_b_rows(self):
+        """How many different rows of B this rank's block references (its compulsory share of B)."""
+        return int(torch.unique(self.colind).numel()) if self.nnz_local else 0
 
     # -- replication of the dense operand -------------------------------------------------------
     def broadcast_B(self, B, K, root=0):
@@ -112,7 +140,54 @@ class RowShardedSpMM:
     # -- the local product -----------------------------------------------------------------------
     def forward(self, B_full):
         """C[row_lo:row_hi, :] for this rank."""
-        return self.spmm_fn(self.rowptr, self.colind, self.val, B_full)
+        if self.spmm_fn is not None:
+            return self.spmm_fn(self.rowptr, self.colind, self.val, B_full)
+        return _cuda_spmm(self.rowptr, self.colind, self.val, B_full, self.max_row_nnz)
+
+    # -- replication overlapped with the product: column panels on a communication stream ----------------
+    def forward_replicating(self, B_block, chunks=4, sequential=False, out=None):
+        """C[row_lo:row_hi, :] = A[row block] @ B when B CHANGES EVERY STEP and arrives row-sharded in equal blocks
+        (``even_b_block()`` rows per rank, zero-padded): the replication is not a separate phase.  The local block is
+        re-laid out as ``chunks`` column panels; panel j is all-gathered over NVLink on a communication stream while the
+        product of panel j - 1 (a [N, K / chunks] operand with row stride K / chunks, written into columns
+        [j K / chunks, (j + 1) K / chunks) of C with row stride K -- the C ABI takes strides) runs on the caller's stream.
+        One step then costs about max(all-gather, product) + one panel of the other instead of their sum.
+        K / chunks < 128 takes the narrow-B walkers: pass ``sequential=True`` for the bits of the plain product
+        (GESPMM_FLAG_SEQUENTIAL), else rows of more than one nonzero are re-associated (within ~2e-6 of max|C|)."""
+        from . import capi
+        blk, K = self.even_b_block(), B_block.shape[1]
+        assert B_block.shape[0] == blk and K % chunks == 0 and (K // chunks) % 4 == 0
+        Kc = K // chunks
+        dev = self.device
+        M_loc = self.row_hi - self.row_lo
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_comm_stream"):
+            self._comm_stream = torch.cuda.Stream(device=dev)
+        comm = self._comm_stream
+        # panel-major copies: local [chunks, blk, Kc], assembled [chunks, world * blk, Kc]
+        local = B_block.view(blk, chunks, Kc).permute(1, 0, 2).contiguous()
+        full = torch.empty(chunks, blk * self.world, Kc, dtype=torch.float32, device=dev)
+        C = out if out is not None else torch.empty(M_loc, K, dtype=torch.float32, device=dev)
+        comm.wait_stream(cur)
+        events = []
+        with torch.cuda.stream(comm):
+            for j in range(chunks):
+                if self.world > 1:
+                    dist.all_gather_into_tensor(full[j], local[j], group=self.group)
+                else:
+                    full[j, :blk].copy_(local[j])
+                ev = torch.cuda.Event()
+                ev.record(comm)
+                events.append(ev)
+        local.record_stream(comm); full.record_stream(comm)
+        opts = capi.opts(sequential=sequential, max_row_nnz=self.max_row_nnz)
+        with torch.cuda.device(dev):
+            for j in range(chunks):
+                cur.wait_event(events[j])
+                capi.csr_spmm_f32_ex(M_loc, self.N, Kc, self.nnz_local, self.rowptr.data_ptr(), self.colind.data_ptr(),
+                                     None if self.val is None else self.val.data_ptr(), full[j].data_ptr(), Kc,
+                                     C.data_ptr() + 4 * j * Kc, K, opts, cur.cuda_stream)
+        return C
 
     # -- no replication: B stays row-sharded, the kernel gathers remote rows over NVLink -------------
     def share_B_parts(self, B_local):

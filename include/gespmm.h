@@ -86,11 +86,11 @@ const char *gespmm_error_string(int code);
  * by fp32 re-association only (see gespmm_row_sum_is_sequential below):
  *   - rows longer than GESPMM_LONG_ROW nonzeros are summed in 8 contiguous segments (one per warp
  *     of a CTA; 64 segments across a thread-block cluster from 32768 nonzeros) combined in fixed order;
- *   - for K <= 64 (K % 4 == 0, aligned operands) a warp gathers 2 / 4 / 8 B rows per instruction and
- *     keeps one partial sum per lane group (nonzeros p, p + NG, p + 2 NG, ... of the row), added in a
- *     fixed butterfly order at the row end.  GESPMM_SEQUENTIAL=1 in the environment selects, for
- *     every K, the fastest walker that keeps the sequential order (for K <= 64: lane groups own
- *     disjoint rows; 0.5-1.07x the default's speed on B200, 1.2-2.1x the plain one-row-per-gather walker).
+ *   - for K <= 64 (K % 4 == 0, aligned operands) and for any K <= 16 a warp gathers 2 / 4 / 8 B rows per
+ *     instruction and keeps one partial sum per lane group (nonzeros p, p + NG, p + 2 NG, ... of the row), added
+ *     in a fixed butterfly order at the row end.  GESPMM_FLAG_SEQUENTIAL in gespmm_opts (per call) or
+ *     GESPMM_SEQUENTIAL=1 in the environment (process default) selects, for every K, the fastest walker
+ *     that keeps the sequential order (lane groups own disjoint rows; 0.5-1.07x the default's speed on B200).
  * N is used for argument checking only (colind values are trusted, like the reference).
  */
 int gespmm_csr_spmm_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
@@ -209,10 +209,11 @@ int gespmm_ipc_free(void *dptr);
  * 1 if gespmm_csr_spmm_f32 sums a row of `row_nnz` nonzeros of a product of width K in the reference's
  * strictly sequential CSR order (its result is then bit-identical to the reference kernels'), 0 if the
  * row's sum is re-associated (deterministically): rows longer than GESPMM_LONG_ROW, and -- where the
- * sub-warp walker for narrow B (K <= 64: several nonzeros per warp-wide gather, one partial sum per
- * lane group) is in use -- rows of more than one nonzero.  Assumes the aligned fast path (K, ldb, ldc
- * multiples of 4, 16-byte aligned B and C); other operands always take the sequential walker for rows up
- * to GESPMM_LONG_ROW.  Pure function of its arguments and of the GESPMM_* tuning environment variables.
+ * sub-warp walker for narrow B (K <= 64 in 16-byte slices, any K <= 16 in 4-byte slices: several nonzeros per
+ * warp-wide gather, one partial sum per lane group) is in use -- rows of more than one nonzero.  For K % 4 == 0 it
+ * assumes aligned operands (ldb, ldc multiples of 4, 16-byte aligned B and C); unaligned ones take the sub-warp
+ * walker only up to K = 16 and a sequential walker above.  Pure function of its arguments and of the GESPMM_*
+ * tuning environment as read by the library (gespmm_reload_env).
  * (New: every reference kernel is sequential, pytorch-custom/spmm_kernel.cu:56-59, 165-168.)
  */
 int gespmm_row_sum_is_sequential(int64_t K, int64_t row_nnz);

@@ -41,7 +41,58 @@ for step in $STEPS; do
         note "ncu dram $wl rc=$?"
       done ;;
     regreddit) # register-staged walker (GESPMM_VARIANT=1) next to the ring walker where B is L2-resident
-      timeout 400 python scripts/sweep_narrow.py --workloads reddit,products --Ks 128,256 --variants -1,1 --tasks 0 --valued 0,1 > $O/sweep_regreddit.txt 2> $O/sweep_regreddit.err; note "regreddit rc=$?" ;;
+      timeout 400 python scripts/sweep_narrow.py --workloads reddit,products --Ks 128,256 --variants=-1,1 --tasks 0 --valued 0,1 > $O/sweep_regreddit.txt 2> $O/sweep_regreddit.err; note "regreddit rc=$?" ;;
+    newtests) # round 2: per-call options, fused scaling, row-group kernel for tiny odd K, L2 steering
+      timeout 900 python -m pytest tests/test_spmm_gpu.py -q -m gpu -x -k "sequential_order or fused or longest_row or l2_priority or k_sweep or gcnconv or degenerate or max_reduce or c_abi_strides" > $O/t_new.log 2>&1; note "newtests rc=$?" ;;
+    l2sweep)  # L2 eviction-priority steering of the gathers on the cit-Patents shape (clustered / uniform)
+      timeout 600 python scripts/sweep_l2.py > $O/sweep_l2.txt 2> $O/sweep_l2.err; note "l2sweep rc=$?"
+      timeout 300 python scripts/sweep_l2.py --workloads citpatents --policies 0,22 --windows 131072 --tasks 64,96,128,192 --pads 0,2048,4096 >> $O/sweep_l2.txt 2>> $O/sweep_l2.err; note "l2sweep2 rc=$?" ;;
+    l2ncu)    # DRAM bytes per launch of chosen configurations: L2NCU="policy,window,task,pad ..." (default below)
+      for cfg in ${L2NCU:-0,0,0,0 22,131072,0,0 20,131072,0,0}; do
+        timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct \
+            --clock-control none -k regex:spmm_flat --launch-skip 3 -c 2 --csv --log-file $O/ncu_l2_$cfg.csv \
+            python scripts/sweep_l2.py --workloads citpatents --one $cfg > $O/ncu_l2_$cfg.log 2>&1
+        note "l2ncu $cfg rc=$?"
+      done ;;
+    sanitize_rg) # compute-sanitizer over the row-group kernel (K = 3, 7, 13) through the CLI
+      python - > $O/sanitize_gen.log 2>&1 <<'PY'
+import sys, numpy as np
+sys.path.insert(0, '.')
+import __graft_entry__ as e
+e.load_package()
+from gespmm_b200 import graphs
+rng = np.random.default_rng(0)
+M = 3000
+deg = rng.integers(0, 9, M); deg[rng.random(M) < 0.3] = 0
+deg[[5, 700, 701, 2999]] = [40000, 5000, 4097, 9000]
+deg[100:140] = rng.integers(30, 300, 40)
+rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+colind = rng.integers(0, M, rowptr[-1]).astype(np.int32)
+graphs.write_mtx('gpurun_out/sanitize.mtx', rowptr, colind)
+PY
+      for tool in memcheck racecheck synccheck; do
+        echo "== $tool (K=3,7,13,128)" >> $O/sanitize_rowgroup.txt
+        timeout 300 compute-sanitizer --tool $tool --error-exitcode 9 ge-spmm_b200/bin/spmm_test $O/sanitize.mtx 0 \
+            --K 3,7,13,128 --iters 2 --validate --out $O/sanitize.csv 2>&1 | grep -E "SUMMARY|validate|WA|Error|error" | head -12 >> $O/sanitize_rowgroup.txt
+      done
+      note "sanitize_rg done" ;;
+    probel2)  # which hinted instruction does the hardware refuse?  store only / gathers only / both
+      for pol in 16 32 1 4 5 21; do
+        timeout 120 python scripts/probe_l2.py $pol >> $O/probe_l2.txt 2>&1; echo "policy $pol rc=$?" >> $O/probe_l2.txt
+      done
+      timeout 200 compute-sanitizer --tool memcheck python scripts/probe_l2.py 21 2>&1 | grep -v "^$" | head -40 > $O/probe_l2_sanitizer.txt
+      note "probel2 done" ;;
+    ncurg)    # full capture of the narrow-B kernels at K = 3: sub-warp walker on 4-byte slices (default) and row-group kernel
+      for wl in products citpatents; do
+        for v in -1 4; do
+          timeout 400 ncu --set full --clock-control none --import-source on -k regex:"spmm_rowgroup|spmm_flat" --launch-skip 3 -c 1 \
+              -f -o /tmp/ncu_rg python scripts/sweep.py --workload $wl --K 3 --variants=$v --iters 1 --unvalued > $O/ncu_rg_${wl}_v$v.log 2>&1
+          note "ncurg $wl v$v rc=$?"
+          ncu -i /tmp/ncu_rg.ncu-rep --page raw --csv > $O/ncu_rg_${wl}_v${v}_raw.csv 2>/dev/null
+          ncu -i /tmp/ncu_rg.ncu-rep --page source --csv > $O/ncu_rg_${wl}_v${v}_source.csv 2>/dev/null
+          rm -f /tmp/ncu_rg.ncu-rep
+        done
+      done ;;
     rows)     # sub-warp (2) vs row-parallel (4) narrow walkers on every shape
       timeout 600 python scripts/sweep_narrow.py --variants 2,4 --tasks 0 > $O/sweep_v24.txt 2> $O/sweep_v24.err; note "rows rc=$?" ;;
     auto64)   # the SpMM suite with the sub-warp walker chosen automatically for K <= 64

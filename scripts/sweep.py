@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--ref", action="store_true", help="also time the reference kernel")
     args = ap.parse_args()
     entry.load_package()
-    from gespmm_b200 import graphs
+    from gespmm_b200 import capi, graphs
     from gespmm_b200.op import spmm
     dev = torch.device("cuda:0")
     rowptr, colind = bench.make_graph(args.workload, args.scale, dev)
@@ -44,6 +44,7 @@ def main():
     print("# %s K=%d M=%d nnz=%d" % (args.workload, args.K, M, nnz), flush=True)
     for v, t, l in itertools.product(args.variants.split(","), args.tasks.split(","), args.longs.split(",")):
         os.environ["GESPMM_VARIANT"], os.environ["GESPMM_TASK"], os.environ["GESPMM_LONG"] = v, t, l
+        capi.reload_env()  # the library reads its environment once
         run = (lambda: spmm.csr_spmm_no_edge_value(rowptr, colind, B)) if val is None else (lambda: spmm.csr_spmm(rowptr, colind, val, B))
         for _ in range(3):
             C = run()

@@ -31,7 +31,7 @@ def main():
     ap.add_argument("--ref", action="store_true", help="also time the reference's spmm_test2<float> (oracle/_ref)")
     args = ap.parse_args()
     entry.load_package()
-    from gespmm_b200 import graphs
+    from gespmm_b200 import capi, graphs
     from gespmm_b200.op import spmm
     dev = torch.device("cuda:0")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -47,6 +47,7 @@ def main():
                 for variant in (int(x) for x in args.variants.split(",")):
                     for task in args.tasks.split(","):
                         os.environ["GESPMM_VARIANT"], os.environ["GESPMM_TASK"] = str(variant), task
+                        capi.reload_env()  # the library reads its environment once
                         torch.cuda.empty_cache()
                         run = (lambda: spmm.csr_spmm(rowptr, colind, val, B)) if valued else (lambda: spmm.csr_spmm_no_edge_value(rowptr, colind, B))
                         for _ in range(3):

@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     args = ap.parse_args()
     entry.load_package()
-    from gespmm_b200 import graphs
+    from gespmm_b200 import capi, graphs
     from gespmm_b200.op import spmm
     dev = torch.device("cuda:0")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -37,6 +37,7 @@ def main():
         first = None
         for v in args.Vs.split(","):
             os.environ["GESPMM_PANEL_V"] = v
+            capi.reload_env()  # the library reads its environment once
             for _ in range(3):
                 C = spmm.csr_spmm(rowptr, colind, val, B)
             torch.cuda.synchronize()

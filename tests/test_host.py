@@ -98,13 +98,14 @@ def test_row_sum_order_query(pkg, gespmm_env):
         assert not capi.row_sum_is_sequential(K, capi.LONG_ROW + 1)
         assert capi.row_sum_is_sequential(K, capi.LONG_ROW) == capi.row_sum_is_sequential(K, 2)
     assert capi.row_sum_is_sequential(128, capi.LONG_ROW) and capi.row_sum_is_sequential(68, 2) and capi.row_sum_is_sequential(30, 2)
+    assert not capi.row_sum_is_sequential(3, 2) and not capi.row_sum_is_sequential(7, 2) and capi.row_sum_is_sequential(17, 2)  # 4-byte slices up to K = 16
     gespmm_env.setenv("GESPMM_VARIANT", "0")  # the ring walker: sequential for every K
     assert all(capi.row_sum_is_sequential(K, capi.LONG_ROW) for K in (4, 16, 32, 64))
     gespmm_env.setenv("GESPMM_VARIANT", "2")  # the sub-warp walker wherever it applies: K <= 64, K % 4 == 0
     assert not any(capi.row_sum_is_sequential(K, 2) for K in (4, 16, 32, 48, 64))
-    assert all(capi.row_sum_is_sequential(K, 2) for K in (3, 30, 65, 68, 128))
+    assert all(capi.row_sum_is_sequential(K, 2) for K in (30, 65, 68, 128)) and not capi.row_sum_is_sequential(3, 2)
     gespmm_env.setenv("GESPMM_VARIANT", "4")  # the row-parallel narrow walker: sequential again
-    assert all(capi.row_sum_is_sequential(K, capi.LONG_ROW) for K in (4, 16, 32, 48, 64, 128))
+    assert all(capi.row_sum_is_sequential(K, capi.LONG_ROW) for K in (3, 4, 7, 16, 32, 48, 64, 128))
     gespmm_env.setenv("GESPMM_VARIANT", "2")
     gespmm_env.setenv("GESPMM_SEQUENTIAL", "1")  # wins over GESPMM_VARIANT
     assert all(capi.row_sum_is_sequential(K, capi.LONG_ROW) for K in (4, 16, 32, 48, 64, 128))

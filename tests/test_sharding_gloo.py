@@ -53,6 +53,23 @@ def _worker(rank, world, port, valued, out_dir):
         assert torch.equal(B2, B)
         C_local2 = sh.forward(B2)
         assert torch.equal(C_local2, C_local)
+        # (3) B row-sharded in EQUAL blocks (what each rank uploads in the end-to-end path): one all_gather_into_tensor
+        #     into a padded buffer whose first N rows are B (gloo has no all_gather_into_tensor: emulate it with all_gather)
+        blk = sh.even_b_block()
+        assert blk * world >= N > blk * (world - 1)
+        lo, hi = min(N, rank * blk), min(N, (rank + 1) * blk)
+        mine = torch.zeros(blk, K)
+        mine[: hi - lo] = B[lo:hi]
+        if dist.get_backend() == "gloo":
+            pieces = [torch.empty(blk, K) for _ in range(world)]
+            dist.all_gather(pieces, mine)
+            B3 = torch.cat(pieces)[:N]
+        else:
+            B3 = sh.all_gather_B_even(mine)
+        assert torch.equal(B3, B)
+        # (4) the rank's compulsory share of B and its longest row
+        assert sh.distinct_b_rows() == int(torch.unique(sh.colind).numel()) <= N
+        assert sh.max_row_nnz == -1   # only measured for device-resident blocks (the CUDA path)
         if rank == 0:
             want = oracle.spmm(rowptr.numpy(), colind.numpy(), None if val is None else val.numpy(), B.numpy())
             assert np.array_equal(full.numpy(), want)

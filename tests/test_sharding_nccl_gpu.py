@@ -51,6 +51,22 @@ def _worker(rank, world, port, out_dir):
         torch.cuda.synchronize()
         assert torch.equal(C_fused, C_local), "sharded-B fused product must equal the replicated-B product bit for bit"
         sh.release_B_parts()
+        # B row-sharded in equal blocks: one all-gather; and the replication overlapped with the product, panel by panel
+        blk = sh.even_b_block()
+        lo, hi = min(N, rank * blk), min(N, (rank + 1) * blk)
+        even = torch.zeros(blk, K, device=dev)
+        even[: hi - lo] = B[lo:hi]
+        assert torch.equal(sh.all_gather_B_even(even), B)
+        for chunks in (1, 2, 4):
+            C_pipe = sh.forward_replicating(even, chunks=chunks, sequential=True)
+            torch.cuda.synchronize()
+            short_loc = (sh.rowptr[1:] - sh.rowptr[:-1]) <= capi.LONG_ROW
+            assert torch.equal(C_pipe[short_loc], C_local[short_loc]), "pipelined replication (sequential order) must give the plain product's bits"
+            assert torch.allclose(C_pipe, C_local, rtol=1e-4, atol=1e-3)
+        C_pipe = sh.forward_replicating(even, chunks=4)
+        torch.cuda.synchronize()
+        assert torch.allclose(C_pipe, C_local, rtol=1e-4, atol=1e-3)
+        assert sh.max_row_nnz == int((sh.rowptr[1:] - sh.rowptr[:-1]).max())
         full = sh.gather_C(C_local, dst=0)
         if rank == 0:
             want = oracle.spmm(rowptr.numpy(), colind.numpy(), val.numpy(), B.cpu().numpy())

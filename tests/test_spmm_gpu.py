@@ -225,13 +225,15 @@ def test_subwarp_walker_for_narrow_B(spmm, dev, oracle, pkg, gespmm_env, K):
                               C.data_ptr(), K, -10000.0, torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         assert np.array_equal(C.cpu().numpy(), oracle.spmm_max(rowptr, colind, None if vv is None else vf, Bf, init=-10000.0))
-    # not a multiple of 4 / unaligned: the request is ignored, the sequential scalar walker runs
-    gespmm_env.setenv("GESPMM_VARIANT", "2")
+    # not a multiple of 4: up to K = 16 the same walker runs on 4-byte slices (re-associated, within tolerance; exact on
+    # integer-valued operands), above that the sequential scalar walker (bit-identical)
     B3 = rng.standard_normal((N, K - 1)).astype(np.float32)
-    C = _run(spmm, dev, rowptr, colind, None, B3).cpu().numpy()
-    want = oracle.spmm(rowptr, colind, None, B3)
-    short = np.diff(rowptr) <= LONG
-    assert np.array_equal(C[short], want[short])
+    assert capi.row_sum_is_sequential(K - 1, 2) == (K - 1 > 16)
+    for v in (None, vf):
+        _check(oracle, rowptr, colind, v, B3, _run(spmm, dev, rowptr, colind, v, B3))
+    B3i = rng.integers(-8, 9, (N, K - 1)).astype(np.float32)
+    for v in (None, vi):
+        assert np.array_equal(_run(spmm, dev, rowptr, colind, v, B3i).cpu().numpy(), oracle.spmm(rowptr, colind, v, B3i, fma=True))
 
 
 @pytest.mark.parametrize("K", [4, 8, 16, 24, 32, 36, 48, 64])
@@ -266,6 +268,117 @@ def test_row_parallel_walker_for_narrow_B_is_sequential(spmm, dev, oracle, pkg, 
                               C.data_ptr(), K, -10000.0, torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         assert np.array_equal(C.cpu().numpy(), oracle.spmm_max(rowptr, colind, None if vv is None else vf, Bf, init=-10000.0))
+
+
+def _mixed_graph(rng, M=2600, N=3000):
+    """Empty rows, short rows, a block of medium rows, long (> 4096) and huge (>= 32768) rows."""
+    deg = rng.integers(0, 9, M)
+    deg[rng.random(M) < 0.3] = 0
+    deg[[5, 6, 900, M - 1]] = [40000, 4097, 3000, 33000]
+    deg[1000:1100] = rng.integers(20, 400, 100)
+    rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    colind = rng.integers(0, N, int(rowptr[-1])).astype(np.int32)
+    return rowptr, colind, M, N
+
+
+@pytest.mark.parametrize("K", [3, 4, 7, 13, 16, 32, 48, 64])
+def test_sequential_order_is_a_per_call_option(spmm, dev, oracle, pkg, K):
+    """csr_spmm_ex(sequential=True) -> GESPMM_FLAG_SEQUENTIAL: bit-identical to the oracle on every row up to
+    GESPMM_LONG_ROW at the widths whose default walker re-associates; the plain call next to it, same process, same
+    environment, is not affected (the order is no longer a process-wide switch)."""
+    from gespmm_b200 import capi
+    rng = np.random.default_rng(900 + K)
+    rowptr, colind, M, N = _mixed_graph(rng)
+    Bf = rng.standard_normal((N, K)).astype(np.float32)
+    vf = rng.standard_normal(len(colind)).astype(np.float32)
+    rp, ci, vd, Bd = (torch.as_tensor(x, device=dev) for x in (rowptr, colind, vf, Bf))
+    short = np.diff(rowptr) <= LONG
+    assert capi.row_sum_is_sequential(K, LONG, capi.opts(sequential=True)) and not capi.row_sum_is_sequential(K, 2)
+    for v, vnp in ((None, None), (vd, vf)):
+        Cs = spmm.csr_spmm_ex(rp, ci, v, Bd, sequential=True)
+        Cd = spmm.csr_spmm_ex(rp, ci, v, Bd)
+        torch.cuda.synchronize()
+        want = oracle.spmm(rowptr, colind, vnp, Bf, fma=True)
+        assert np.array_equal(Cs.cpu().numpy()[short], want[short])
+        plain = spmm.csr_spmm_no_edge_value(rp, ci, Bd) if v is None else spmm.csr_spmm(rp, ci, v, Bd)
+        assert torch.equal(Cd, plain)
+        _check(oracle, rowptr, colind, vnp, Bf, Cd)
+
+
+@pytest.mark.parametrize("K", [3, 7, 8, 16, 32, 41, 64, 100, 128, 200, 256])
+def test_fused_scales_and_bias_match_the_separate_passes_bitwise(spmm, dev, oracle, pkg, K):
+    """gespmm_opts.row_scale / col_scale / bias (GCNConv's passes around the aggregation, pytorch-custom/op.py:142-147):
+    out = (A @ (B * cs)) * rs + bias must carry the bits of the four separate passes -- every product and sum is rounded
+    separately, in that order -- for every walker (ring, sub-warp, row-parallel, scalar), valued and unvalued, on empty,
+    short, long and huge rows, and with any subset of the three vectors."""
+    rng = np.random.default_rng(1200 + K)
+    rowptr, colind, M, N = _mixed_graph(rng)
+    Bf = rng.standard_normal((N, K)).astype(np.float32)
+    vf = rng.standard_normal(len(colind)).astype(np.float32)
+    rs = (1.0 / np.sqrt(1.0 + np.diff(rowptr))).astype(np.float32)
+    cs = (0.25 + rng.random(N)).astype(np.float32)
+    bias = rng.standard_normal(K).astype(np.float32)
+    rp, ci, vd, Bd, rsd, csd, bd = (torch.as_tensor(x, device=dev) for x in (rowptr, colind, vf, Bf, rs, cs, bias))
+    short = np.diff(rowptr) <= LONG
+    for sequential in (False, True):
+        for v, vnp in ((None, None), (vd, vf)):
+            for use in ((1, 1, 1), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0)):
+                r_, c_, b_ = (rsd if use[0] else None), (csd if use[1] else None), (bd if use[2] else None)
+                got = spmm.csr_spmm_ex(rp, ci, v, Bd, sequential=sequential, row_scale=r_, col_scale=c_, bias=b_)
+                x = Bd * csd[:, None] if use[1] else Bd
+                y = spmm.csr_spmm_ex(rp, ci, v, x.contiguous(), sequential=sequential)
+                if use[0]:
+                    y = y * rsd[:, None]
+                if use[2]:
+                    y = y + bd
+                torch.cuda.synchronize()
+                assert torch.equal(got, y), "fused != separate passes (K=%d sequential=%s valued=%s use=%s)" % (K, sequential, v is not None, use)
+        from gespmm_b200 import capi
+        if capi.row_sum_is_sequential(K, 2, capi.opts(sequential=sequential)):   # against the oracle, on the rows summed in CSR order
+            xs = (Bf * cs[:, None]).astype(np.float32)
+            want = (oracle.spmm(rowptr, colind, vf, xs, fma=True) * rs[:, None]).astype(np.float32) + bias
+            got = spmm.csr_spmm_ex(rp, ci, vd, Bd, sequential=sequential, row_scale=rsd, col_scale=csd, bias=bd).cpu().numpy()
+            assert np.array_equal(got[short], want[short])
+
+
+def test_longest_row_lets_the_call_skip_the_long_row_kernel(spmm, dev, oracle, pkg):
+    """gespmm_max_row_nnz + gespmm_opts.max_row_nnz: same bits with and without the hint; a graph with long rows still
+    gets its long-row kernel when the hint says so."""
+    rng = np.random.default_rng(77)
+    rowptr, colind = _rand_csr(rng, 20000, 20000, 90000, empty_frac=0.3)
+    rowptr2, colind2, M2, N2 = _mixed_graph(rng)
+    for rpn, cin, N in ((rowptr, colind, 20000), (rowptr2, colind2, N2)):
+        rp, ci = torch.as_tensor(rpn, device=dev), torch.as_tensor(cin, device=dev)
+        B = torch.randn(N, 128, device=dev)
+        mx = spmm.max_row_nnz(rp)
+        assert mx == int(np.diff(rpn).max())
+        a = spmm.csr_spmm_ex(rp, ci, None, B, max_row_nnz=mx)
+        b = spmm.csr_spmm_no_edge_value(rp, ci, B)
+        torch.cuda.synchronize()
+        assert torch.equal(a, b)
+    assert spmm.max_row_nnz(torch.zeros(1, dtype=torch.int32, device=dev)) == 0
+
+
+@pytest.mark.parametrize("policy", [1 + 4 * 1 + 16 * 1, 2 + 4 * 1 + 16 * 1, 0 + 4 * 1, 3 + 4 * 3 + 16 * 3])
+def test_l2_priority_steering_does_not_change_results(dev, oracle, pkg, policy):
+    """gespmm_opts.l2_policy: the gathers and stores carry L2 eviction priorities; the sums are the same bits."""
+    from gespmm_b200 import capi
+    rng = np.random.default_rng(31)
+    rowptr, colind, M, N = _mixed_graph(rng)
+    nnz = len(colind)
+    for K in (128, 200, 256):
+        Bf = rng.standard_normal((N, K)).astype(np.float32)
+        vf = rng.standard_normal(nnz).astype(np.float32)
+        rp, ci, vd, Bd = (torch.as_tensor(x, device=dev) for x in (rowptr, colind, vf, Bf))
+        st = torch.cuda.current_stream().cuda_stream
+        for v in (None, vd):
+            C0 = torch.empty(M, K, device=dev); C1 = torch.full((M, K), float("nan"), device=dev)
+            vp = None if v is None else v.data_ptr()
+            capi.csr_spmm_f32(M, N, K, nnz, rp.data_ptr(), ci.data_ptr(), vp, Bd.data_ptr(), K, C0.data_ptr(), K, st)
+            capi.csr_spmm_f32_ex(M, N, K, nnz, rp.data_ptr(), ci.data_ptr(), vp, Bd.data_ptr(), K, C1.data_ptr(), K,
+                                 capi.opts(l2_policy=policy, l2_window_rows=500), st)
+            torch.cuda.synchronize()
+            assert torch.equal(C0, C1)
 
 
 def test_skewed_rmat_graph(spmm, dev, oracle, pkg):
@@ -557,29 +670,42 @@ def test_gcnconv_matches_dense(dev, pkg):
     assert x.grad is not None and conv.weight.grad is not None and torch.isfinite(x.grad).all()
 
 
-def test_gcnconv_fused_norm_and_training_loop(dev, pkg):
-    """fuse_norm folds the degree normalisation into the valued kernel's edge weights: same layer output;
-    the 2-layer training loop (the reference's gcn_custom.py on the real PubMed adjacency) learns."""
+def test_gcnconv_fused_norm_and_training_loop(dev, pkg, golden_csr, tmp_path):
+    """fuse_norm runs both degree normalisations and the bias add inside the kernel (gespmm_opts.row_scale / col_scale /
+    bias): the layer's output and its gradients carry the BITS of the unfused layer (op.py:142-147), valued and unvalued;
+    the 2-layer training loop (the reference's gcn_custom.py, on the real PubMed adjacency read from a .mtx) learns."""
     import importlib.util
+    from gespmm_b200 import graphs
     from gespmm_b200.op import GCNConv
     spec = importlib.util.spec_from_file_location("gcn_custom", os.path.join(ROOT, "ge-spmm_b200", "gcn_custom.py"))
     gcn = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(gcn)
-    g, x, y, masks, n_in, n_out = gcn.load_problem(dev)
-    a = (g["rowptr"], g["colind"], g["colptr"], g["rowind"], g["value_csr"], g["value_csc"])
-    torch.manual_seed(1)
-    plain = GCNConv(n_in, 32, cached=True).to(dev)
-    fused = GCNConv(n_in, 32, cached=True, fuse_norm=True).to(dev)
-    fused.load_state_dict(plain.state_dict())
-    xg1, xg2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
-    o1, o2 = plain(xg1, *a), fused(xg2, *a)
-    assert torch.allclose(o1, o2, rtol=1e-4, atol=1e-6)
-    o1.square().sum().backward(); o2.square().sum().backward()
-    assert torch.allclose(xg1.grad, xg2.grad, rtol=1e-3, atol=1e-7)
-    assert torch.allclose(plain.weight.grad, fused.weight.grad, rtol=1e-3, atol=1e-6)
+    rowptr, colind, shape = golden_csr("pubmed")
+    mtx = str(tmp_path / "pubmed.mtx")
+    graphs.write_mtx(mtx, rowptr, colind, N=shape[1])
+    g, x, y, masks, n_in, n_out = gcn.load_problem(dev, mtx=mtx)
+    assert g["rowptr"].numel() - 1 == 19717 and g["colind"].numel() == 88648 + 19717  # + self-loops
+    for valued in (True, False):
+        a = (g["rowptr"], g["colind"], g["colptr"], g["rowind"]) + ((g["value_csr"], g["value_csc"]) if valued else ())
+        for width in (32, 128, 3):
+            torch.manual_seed(1)
+            plain = GCNConv(n_in, width, cached=True).to(dev)
+            fused = GCNConv(n_in, width, cached=True, fuse_norm=True).to(dev)
+            with torch.no_grad():
+                plain.bias.uniform_(-1, 1)
+            fused.load_state_dict(plain.state_dict())
+            xg1, xg2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+            o1, o2 = plain(xg1, *a), fused(xg2, *a)
+            assert torch.equal(o1, o2), "fused layer output must be bit-identical (width %d, valued %s)" % (width, valued)
+            w = torch.randn_like(o1)
+            (o1 * w).sum().backward(); (o2 * w).sum().backward()
+            assert torch.equal(xg1.grad, xg2.grad) and torch.equal(plain.weight.grad, fused.weight.grad)
+            assert torch.allclose(plain.bias.grad, fused.bias.grad, rtol=1e-5, atol=1e-5)
     for fuse in (False, True):
-        res = gcn.run(n_hidden=16, layers=2, epochs=40, fuse_norm=fuse, log=lambda *_: None)
+        res = gcn.run(n_hidden=16, layers=2, epochs=40, fuse_norm=fuse, log=lambda *_: None, mtx=mtx)
         assert res["last_loss"] < 0.7 * res["first_loss"] and res["best_val"] > 0.5, res
+    res = gcn.run(n_hidden=16, layers=2, epochs=5, fuse_norm=True, log=lambda *_: None)  # the synthetic default graph
+    assert res["last_loss"] == res["last_loss"]
 
 
 # ---- CLI ---------------------------------------------------------------------------------------------
