@@ -624,7 +624,7 @@ def main():
         remote_frac = t[0] / t[1]
 
         def step():
-            return sh.forward_sharded_B(parts, K)
+            return sh.forward_sharded_B(parts, K, force=True)
     else:
         def step():
             return sh.forward(B)

@@ -27,7 +27,7 @@ SYMBOLS = (
 _lib = None
 
 FLAG_SEQUENTIAL, FLAG_NO_OVERLAP = 0x1, 0x2
-WALKER_AUTO, WALKER_RING, WALKER_REGISTER, WALKER_SUBWARP, WALKER_ROWS = 0, 1, 2, 3, 4
+WALKER_AUTO, WALKER_RING, WALKER_REGISTER, WALKER_SUBWARP, WALKER_ROWS, WALKER_BULK = 0, 1, 2, 3, 4, 5
 
 
 class Opts(ctypes.Structure):

@@ -389,9 +389,30 @@ __device__ __forceinline__ void cp_async16(unsigned saddr, const void *g)
     if (CP == 1) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(g) : "memory");
     else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(g) : "memory");
 }
-__device__ __forceinline__ void cp_async16_hint(unsigned saddr, const void *g, unsigned long long pol)
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier ---------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
 {
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(g), "l"(pol) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+                 "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(unsigned dst, const void *src, unsigned bytes, unsigned bar, unsigned long long pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -461,7 +482,7 @@ struct WalkerRing {
     // HINT
     unsigned long long pol_near, pol_far, pol_store;
     int window, cur_row;
-    bool hint_gather, hint_store;  // a priority code of 0 everywhere = the plain instruction (no descriptor)
+    bool hint_store;            // store priority 0 = the plain streaming store
 
     static constexpr int kPanel = 128 * V;
     __device__ __forceinline__ void init(const Operands &o, int panel, int K, int ln, unsigned ring_base) {
@@ -484,7 +505,7 @@ struct WalkerRing {
         if constexpr (HINT) {
             pol_near = l2_policy(o.l2_near); pol_far = l2_policy(o.l2_far); pol_store = l2_policy(o.l2_store);
             window = o.l2_window; cur_row = 0;
-            hint_gather = (o.l2_near | o.l2_far) != 0; hint_store = o.l2_store != 0;
+            hint_store = o.l2_store != 0;
         }
     }
     __device__ __forceinline__ void finish(T (&)[V]) const {}
@@ -502,9 +523,6 @@ struct WalkerRing {
             for (int i = 1; i < kMaxParts; i++) q += (i < peer->parts && c >= peer->lo[i]) ? 1 : 0;
             return (unsigned long long)reinterpret_cast<uintptr_t>(peer->base[q]) +
                    (unsigned long long)(unsigned)(c - peer->lo[q]) * ldb_bytes;
-        } else if constexpr (HINT) {
-            const int d = c - cur_row;
-            return ((d < 0 ? -d : d) > window) ? (c | (int)0x80000000) : c;
         } else {
             return c;
         }
@@ -543,15 +561,11 @@ struct WalkerRing {
 #pragma unroll
         for (int i0 = 0; i0 < G; i0 += UB) {
             const char *bp[UB];
-            [[maybe_unused]] unsigned long long pol[UB];
 #pragma unroll
             for (int i = 0; i < UB; i++) {
                 const Tok t = __shfl_sync(kFull, cols, pos0 + i0 + i);
                 if constexpr (PEER) bp[i] = reinterpret_cast<const char *>((uintptr_t)(t + lane_off));
-                else if constexpr (HINT) {
-                    bp[i] = Bl + (unsigned long long)((unsigned)t & 0x7fffffffu) * ldb_bytes;
-                    pol[i] = t < 0 ? pol_far : pol_near;
-                } else bp[i] = Bl + (unsigned long long)(unsigned)t * ldb_bytes;
+                else bp[i] = Bl + (unsigned long long)(unsigned)t * ldb_bytes;
             }
 #pragma unroll
             for (int i = 0; i < UB; i++) {
@@ -559,10 +573,10 @@ struct WalkerRing {
 #pragma unroll
                     for (int v = 0; v < V; v++) {
                         if (pack_on(v)) {
-                            if constexpr (HINT) {
-                                if (hint_gather) cp_async16_hint(ring + slot + ((i0 + i) * V + v) * 512, bp[i] + v * 512, pol[i]);
-                                else cp_async16<CP>(ring + slot + ((i0 + i) * V + v) * 512, bp[i] + v * 512);
-                            } else cp_async16<CP>(ring + slot + ((i0 + i) * V + v) * 512, bp[i] + v * 512);
+                            // (cp.async with an L2 cache-hint operand assembles -- LDGSTS with a policy descriptor -- but
+                            // traps as an illegal instruction on sm_100a, profiles/r02_ldgsts_cache_hint_illegal_instruction.txt:
+                            // per-gather priorities are the bulk walker's business)
+                            cp_async16<CP>(ring + slot + ((i0 + i) * V + v) * 512, bp[i] + v * 512);
                         }
                     }
                 }
@@ -662,6 +676,189 @@ struct WalkerRing {
             if constexpr (FUSE) csc = nsc;
         }
         cp_async_wait<0>();
+    }
+};
+
+// =================================================================================================
+// Bulk walker: every gathered B row is ONE TMA bulk copy (cp.async.bulk, SASS UBLKCP) into the ring.
+// =================================================================================================
+// Same flat stream, same ring geometry (8 rows per stage, two stages, 512 bytes per row and 128-column panel) and same
+// consume side as WalkerRing, but the copy side is the Blackwell/Hopper asynchronous proxy:
+//   * the lane that LOADED a nonzero's column issues that row's copy itself -- one 512-byte cp.async.bulk per row, no
+//     shuffle, no per-lane 16-byte LDGSTS through the LSU data pipe (every gathered byte used to cross shared memory's
+//     store path once via LDGSTS and once via LDS; now only the LDS remains);
+//   * completion is an mbarrier per stage slot: lane 0 arrives with the stage's byte count (expect_tx), the copies
+//     complete_tx it, every lane waits on the slot's phase parity before its LDS.128;
+//   * a bulk copy takes an L2 cache-policy operand (HINT): rows whose column lies within `window` rows of the rows being
+//     summed are fetched evict_normal / evict_last, the others evict_first, so that the reuse window of a banded graph
+//     is not pushed out of the L2 by rows that will not be referenced again (LDGSTS cannot carry the operand on sm_100a).
+// Sum only, B in one array, K % 4 == 0 and aligned operands (a bulk copy needs 16-byte aligned addresses and sizes).
+template <bool VALUED, bool MASKED, bool HINT>
+struct WalkerBulk {
+    using P = Pack<true>;
+    using T = float4;
+    using R = Reduce<P, VALUED, false, false>;
+    static constexpr bool kFuse = false;
+    static constexpr int G = 8, NS = 2, S32 = 32 / G, UB = 4;
+    static constexpr int kStageBytes = G * 512;
+    static constexpr int kRingBytes = NS * kStageBytes + 16;  // per warp: the ring + one mbarrier per slot
+    static constexpr int kPanel = 128;
+    static_assert((S32 & 1) == 0, "stage s of every chunk must land in slot s & 1");
+
+    const int *__restrict__ colind;
+    const float *__restrict__ val;
+    const char *__restrict__ Bp;  // B + the panel's first column (byte pointer; the same for every lane)
+    float *__restrict__ Cl;       // C + this lane's 4 columns
+    unsigned ldb_bytes, row_bytes;
+    int ldc, lane;
+    bool on;                      // this lane's 4 columns lie inside K
+    unsigned ring, ring_lane, bar;
+    unsigned phase;               // bit s: the parity the next wait on slot s expects
+    int slot_out;                 // slot of the one stage that is issued but not yet waited for
+    unsigned long long pol_near, pol_far, pol_store;
+    int window, cur_row;
+    bool hint_store;
+
+    __device__ __forceinline__ T start() const { return P::zero(); }
+
+    __device__ __forceinline__ void init(const Operands &o, int panel, int K, int ln, unsigned ring_base) {
+        const int col0 = panel * kPanel + ln * 4;
+        on = col0 < K;
+        colind = o.colind; val = o.val;
+        Bp = reinterpret_cast<const char *>(o.B + panel * kPanel);
+        Cl = o.C + col0;
+        ldb_bytes = (unsigned)o.ldb * 4u; ldc = o.ldc; lane = ln;
+        row_bytes = (unsigned)min(kPanel, K - panel * kPanel) * 4u;
+        ring = ring_base; ring_lane = ring_base + ln * 16; bar = ring_base + NS * kStageBytes;
+        phase = 0; slot_out = 0;
+        if (ln == 0) { mbar_init(bar, 1); mbar_init(bar + 8, 1); }
+        mbar_init_fence();
+        __syncwarp();
+        if constexpr (HINT) {
+            pol_near = l2_policy(o.l2_near); pol_far = l2_policy(o.l2_far); pol_store = l2_policy(o.l2_store);
+            window = o.l2_window; cur_row = 0; hint_store = o.l2_store != 0;
+        }
+    }
+    __device__ __forceinline__ void finish(T (&)[1]) const {}
+    __device__ __forceinline__ void load_rows(int, int) {}
+
+    // a lane's token for the nonzero it loaded: the column, bit 31 set when the row is "far" (HINT)
+    __device__ __forceinline__ int load_tok(int p) const {
+        const int c = __ldcs(colind + p);
+        if constexpr (HINT) {
+            const int d = c - cur_row;
+            return ((d < 0 ? -d : d) > window) ? (c | (int)0x80000000) : c;
+        } else {
+            return c;
+        }
+    }
+
+    __device__ __forceinline__ void store_row(int rb, int rel, const T (&acc)[1]) const {
+        float *c = Cl + (long long)(rb + rel) * ldc;
+        if (!MASKED || on) {
+            if constexpr (HINT) {
+                if (hint_store) st_hint_f4(c, acc[0], pol_store);
+                else P::stcs(c, acc[0]);
+            } else P::stcs(c, acc[0]);
+        }
+    }
+
+    // the copies of the <= G nonzeros at chunk positions [pos0, pos0 + G) of a chunk holding n nonzeros (`toks`: lane i
+    // holds nonzero i of that chunk) into ring slot `slot`; always exactly one arrival on the slot's mbarrier
+    __device__ __forceinline__ void issue(int toks, int pos0, int n, int slot) {
+        const int cnt = max(0, min(G, n - pos0));
+        __syncwarp();  // every lane is done reading what the slot held (the copies below overwrite it)
+        const unsigned b = bar + 8 * slot;
+        if (lane == 0) mbar_arrive_tx(b, (unsigned)cnt * row_bytes);
+        const int my = lane - pos0;
+        const bool mine = my >= 0 && my < cnt;
+        const char *src = Bp + (unsigned long long)((unsigned)toks & 0x7fffffffu) * ldb_bytes;
+        const unsigned dst = ring + slot * kStageBytes + my * 512;
+        if constexpr (HINT) {  // the policy operand is warp-uniform per instruction: one instruction per priority class
+            if (mine && toks < 0) bulk_g2s_hint(dst, src, row_bytes, b, pol_far);
+            if (mine && toks >= 0) bulk_g2s_hint(dst, src, row_bytes, b, pol_near);
+        } else {
+            if (mine) bulk_g2s(dst, src, row_bytes, b);
+        }
+        slot_out = slot;
+    }
+    __device__ __forceinline__ void wait(int slot) {
+        mbar_wait(bar + 8 * slot, (phase >> slot) & 1u);
+        phase ^= 1u << slot;
+    }
+
+    __device__ __forceinline__ void flush(T (&acc)[1], unsigned &rows_left, int rb) const {
+        store_row(rb, __ffs(rows_left) - 1, acc);
+        rows_left &= rows_left - 1;
+        acc[0] = start();
+    }
+
+    template <bool FULL>
+    __device__ __forceinline__ void consume_impl(float vals, int pos0, int n, unsigned endmask, T (&acc)[1], unsigned &rows_left,
+                                                 int rb, int slot) const {
+#pragma unroll
+        for (int i0 = 0; i0 < G; i0 += UB) {
+            T b[UB];
+            float a[UB];
+#pragma unroll
+            for (int i = 0; i < UB; i++) {
+                if (VALUED) a[i] = __shfl_sync(kFull, vals, pos0 + i0 + i);
+                if ((FULL || pos0 + i0 + i < n) && (!MASKED || on)) b[i] = lds128(ring_lane + slot * kStageBytes + (i0 + i) * 512);
+            }
+            const unsigned ends = (endmask >> (pos0 + i0)) & ((1u << UB) - 1u);
+            if (FULL && ends == 0u) {
+#pragma unroll
+                for (int i = 0; i < UB; i++) R::step(acc[0], VALUED ? a[i] : 1.f, b[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < UB; i++) {
+                    if (FULL || pos0 + i0 + i < n) {
+                        R::step(acc[0], VALUED ? a[i] : 1.f, b[i]);
+                        if (ends & (1u << i)) flush(acc, rows_left, rb);
+                    }
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void consume(float vals, int pos0, int n, unsigned endmask, T (&acc)[1], unsigned &rows_left,
+                                            int rb, int slot) const {
+        if (pos0 + G <= n) consume_impl<true>(vals, pos0, n, endmask, acc, rows_left, rb, slot);
+        else consume_impl<false>(vals, pos0, n, endmask, acc, rows_left, rb, slot);
+    }
+
+    // same contract as WalkerRing::stream
+    __device__ __forceinline__ void stream(int s, int e, T (&acc)[1], int my_end, unsigned rows, int rb) {
+        if constexpr (HINT) cur_row = rb;
+        int ccol = 0, ncol = 0, fcol = 0;
+        float cval = 1.f, nval = 1.f;
+        if (s + lane < e) {
+            ccol = load_tok(s + lane);
+            if (VALUED) cval = __ldcs(val + s + lane);
+        }
+        if (s + 32 + lane < e) ncol = load_tok(s + 32 + lane);
+        const bool my_row = (rows >> lane) & 1u;
+        unsigned rows_left = rows;
+        issue(ccol, 0, min(32, e - s), 0);
+#pragma unroll 1
+        for (int p0 = s; p0 < e; p0 += 32) {
+            if (p0 + 64 + lane < e) fcol = load_tok(p0 + 64 + lane);
+            if (VALUED && p0 + 32 + lane < e) nval = __ldcs(val + p0 + 32 + lane);
+            const unsigned rel = (unsigned)(my_end - 1 - p0);
+            const unsigned endmask = __reduce_or_sync(kFull, (my_row && rel < 32u) ? (1u << rel) : 0u);
+            const int n = min(32, e - p0);
+            const int n_next = e - p0 - 32;
+#pragma unroll 1
+            for (int j = 0; j < S32; j++) {
+                if (j * G >= n) break;  // only in the last chunk; the stage issued last is empty
+                const int jj = j + 1;   // stage whose copies are issued now
+                const bool nxt = jj >= S32;
+                issue(nxt ? ncol : ccol, (jj & (S32 - 1)) * G, nxt ? n_next : n, jj & 1);
+                wait(j & 1);
+                consume(cval, j * G, n, endmask, acc, rows_left, rb, j & 1);
+            }
+            ccol = ncol; ncol = fcol; cval = nval;
+        }
+        wait(slot_out);  // the (empty) stage issued last: every arrival has been waited for when the stream returns
     }
 };
 
@@ -1590,6 +1787,7 @@ constexpr int kL2WindowDefault = 1 << 17;  // rows: 64 MB of 512-byte panel rows
 //   GESPMM_VARIANT unset / < 0 : automatic -- the sub-warp walker for K <= GESPMM_SUBWARP_MAX_K, else the ring walker
 //     0 ring walker (sequential order for every K)   1 register-staged walker (comparisons)
 //     2 sub-warp walker wherever it applies (K <= 64)   4 row-parallel narrow walker wherever it applies (sequential)
+//     5 bulk walker (one TMA bulk copy per gathered row) for K > 64
 //   GESPMM_SEQUENTIAL=1 : the fastest walker that keeps the reference's order for every K (= variant 4)
 //   GESPMM_TASK / GESPMM_LONG / GESPMM_PANEL_V / GESPMM_OVERLAP / GESPMM_SMEM_PAD : launch-shape overrides
 //   GESPMM_L2_POLICY = near + 4 far + 16 store (each 0 normal, 1 evict_first, 2 evict_last, 3 unchanged), GESPMM_L2_WINDOW rows
@@ -1603,6 +1801,7 @@ int walker_of_variant(int variant)
         case 1: return GESPMM_WALKER_REGISTER;
         case 2: return GESPMM_WALKER_SUBWARP;
         case 4: return GESPMM_WALKER_ROWS;
+        case 5: return GESPMM_WALKER_BULK;
         default: return GESPMM_WALKER_AUTO;
     }
 }
@@ -1779,6 +1978,10 @@ cudaError_t dispatch_all(int mode, bool vec4, bool peer, int walker, bool hint, 
     if (mode == 1) return dispatch_ring<VALUED, false, true>(V, a, masked);
     if (mode == 2) return launch_ring<1, VALUED, false, false, true, false>(a, masked);  // V == 1 (see run_spmm)
     if (walker == GESPMM_WALKER_REGISTER) return dispatch_reg4<VALUED>(V, a);
+    if (walker == GESPMM_WALKER_BULK && V == 1) {
+        if (hint) return masked ? launch<WalkerBulk<VALUED, true, true>, 1, true, 24>(a) : launch<WalkerBulk<VALUED, false, true>, 1, true, 24>(a);
+        return masked ? launch<WalkerBulk<VALUED, true, false>, 1, true, 24>(a) : launch<WalkerBulk<VALUED, false, false>, 1, true, 24>(a);
+    }
     if (hint && V == 1) return launch_ring<1, VALUED, false, false, false, true>(a, masked);
     return dispatch_ring<VALUED, false, false>(V, a, masked);
 }
@@ -1851,14 +2054,15 @@ int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr
     // Task window (keys per task).  A task's start-up (row search, first rowptr / colind fetch) is
     // amortised over its window, but its rows are walked 32 at a time, so the best window grows with
     // the average row: measured optima on B200 are ~96 keys at 5 keys/row (cit-Patents shape, at 2.5 M
-    // to 20 M keys), ~256 at 21 (R-MAT), 512-1024 at ~500 (Reddit shape), i.e. ~48*sqrt(keys per row);
+    // to 20 M keys: 1.080 ms at 96, 1.096 at 64, 1.103 at 128, 1.157 at 192; profiles/r02_sweep_l2_bulk.txt), ~256 at 21
+    // (R-MAT), 512-1024 at ~500 (Reddit shape), i.e. ~48*sqrt(keys per row);
     // capped so that the grid keeps at least ~8 waves of resident CTAs.
     const bool sub = vec4 && parts == 0 && use_subwarp(K, ch.walker);
     const bool rows_walker = vec4 && parts == 0 && use_rows(K, ch.walker);
     const long long total = nnz + M;
     const long long warps_per_wave = 148LL * 24;
     const double keys_per_row = (double)total / (double)M;
-    long long tk = ((long long)(48.0 * sqrt(keys_per_row)) + 31) & ~31LL;
+    long long tk = ((long long)(48.0 * sqrt(keys_per_row)) + 16) & ~31LL;  // nearest multiple of 32 (96 at 5.4 keys per row)
     // the sub-warp walker spends 1/NG of the instructions per nonzero, so a task's start-up weighs NG times more:
     // measured optima are 512 (cit-Patents shape) to 1024 (ogbn-products, R-MAT, Reddit shapes) at K = 16, 32
     if (sub || rows_walker) tk *= (K > 32 ? 2 : (K > 16 ? 4 : 8));

@@ -238,10 +238,18 @@ class RowShardedSpMM:
                     capi.ipc_free(keep[1])
             self._parts_keep = None
 
-    def forward_sharded_B(self, part_ptrs, K, stream=None):
+    def forward_sharded_B(self, part_ptrs, K, stream=None, force=False):
         """C[row_lo:row_hi, :] = A[row block] @ B with B given as row blocks (see share_B_parts): one fused
-        kernel computes and pulls the remote B rows over NVLink; nothing is replicated."""
+        kernel computes and pulls the remote B rows over NVLink; nothing is replicated.
+        Measured on 8 x B200: with one peer the remote 512-byte gathers run at ~640 GB/s and the fused kernel
+        beats replicate-then-multiply on graphs with locality; with three or more peers they fall to ~130 GB/s per rank and
+        replication (all_gather_B_even / forward_replicating) wins everywhere -- so beyond two ranks this path must be
+        asked for explicitly (``force=True``)."""
         from . import capi
+        if self.world > 2 and not force:
+            raise RuntimeError("forward_sharded_B is gated to world_size <= 2 (random 512-byte peer gathers reach only ~130 GB/s "
+                               "per rank with >= 3 peers: DESIGN.md section 5); use forward_replicating / all_gather_B_even + forward, "
+                               "or pass force=True")
         bb = self.b_row_bounds()
         M_loc = self.row_hi - self.row_lo
         C = torch.empty(M_loc, K, dtype=torch.float32, device=self.device)

@@ -140,6 +140,8 @@ int gespmm_csr_spmm_max_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
 #define GESPMM_WALKER_REGISTER  2     /* register-staged gathers (no shared memory), sequential order           */
 #define GESPMM_WALKER_SUBWARP   3     /* K <= 64: 2 / 4 / 8 nonzeros per warp-wide copy, re-associated           */
 #define GESPMM_WALKER_ROWS      4     /* K <= 64: lane groups own disjoint rows, sequential order                */
+#define GESPMM_WALKER_BULK      5     /* K > 64: one TMA bulk copy (cp.async.bulk + mbarrier) per gathered row,
+                                         sequential order; the only walker whose gathers can carry l2_policy        */
 
 typedef struct gespmm_opts {
     uint32_t struct_size;    /* sizeof(gespmm_opts), set by gespmm_opts_init (ABI versioning)                    */

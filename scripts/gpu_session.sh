@@ -43,17 +43,29 @@ for step in $STEPS; do
     regreddit) # register-staged walker (GESPMM_VARIANT=1) next to the ring walker where B is L2-resident
       timeout 400 python scripts/sweep_narrow.py --workloads reddit,products --Ks 128,256 --variants=-1,1 --tasks 0 --valued 0,1 > $O/sweep_regreddit.txt 2> $O/sweep_regreddit.err; note "regreddit rc=$?" ;;
     newtests) # round 2: per-call options, fused scaling, row-group kernel for tiny odd K, L2 steering
-      timeout 900 python -m pytest tests/test_spmm_gpu.py -q -m gpu -x -k "sequential_order or fused or longest_row or l2_priority or k_sweep or gcnconv or degenerate or max_reduce or c_abi_strides" > $O/t_new.log 2>&1; note "newtests rc=$?" ;;
-    l2sweep)  # L2 eviction-priority steering of the gathers on the cit-Patents shape (clustered / uniform)
+      timeout 900 python -m pytest tests/test_spmm_gpu.py -q -m gpu -x -k "bulk_walker or sequential_order or fused or longest_row or l2_priority or k_sweep or gcnconv or degenerate or max_reduce or c_abi_strides" > $O/t_new.log 2>&1; note "newtests rc=$?" ;;
+    l2sweep)  # ring (cp.async) vs bulk (TMA) walker, and L2 eviction-priority steering of the bulk gathers, cit-Patents shape
       timeout 600 python scripts/sweep_l2.py > $O/sweep_l2.txt 2> $O/sweep_l2.err; note "l2sweep rc=$?"
-      timeout 300 python scripts/sweep_l2.py --workloads citpatents --policies 0,22 --windows 131072 --tasks 64,96,128,192 --pads 0,2048,4096 >> $O/sweep_l2.txt 2>> $O/sweep_l2.err; note "l2sweep2 rc=$?" ;;
-    l2ncu)    # DRAM bytes per launch of chosen configurations: L2NCU="policy,window,task,pad ..." (default below)
-      for cfg in ${L2NCU:-0,0,0,0 22,131072,0,0 20,131072,0,0}; do
+      timeout 300 python scripts/sweep_l2.py --workloads citpatents --walkers 0,5 --policies 0 --tasks 64,96,128,192 --pads 0,2048,4096 >> $O/sweep_l2.txt 2>> $O/sweep_l2.err; note "l2sweep2 rc=$?" ;;
+    bulksweep) # ring vs bulk walker on the other shapes (Reddit / ogbn-products / R-MAT at half size), K = 128, 256
+      for wl in reddit products rmat; do
+        timeout 300 python scripts/sweep_l2.py --workloads $wl --K 128 --walkers 0,5 --policies 0 --iters 5 --batches 3 >> $O/sweep_bulk.txt 2>> $O/sweep_bulk.err
+        timeout 300 python scripts/sweep_l2.py --workloads $wl --K 256 --walkers 0,5 --policies 0 --iters 5 --batches 3 >> $O/sweep_bulk.txt 2>> $O/sweep_bulk.err
+      done; note "bulksweep rc=$?" ;;
+    l2ncu)    # DRAM bytes per launch of chosen configurations: L2NCU="walker,policy,window,task,pad ..." (default below)
+      for cfg in ${L2NCU:-0,0,0,0,0 5,0,0,0,0 5,22,131072,0,0 5,20,131072,0,0}; do
         timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct \
             --clock-control none -k regex:spmm_flat --launch-skip 3 -c 2 --csv --log-file $O/ncu_l2_$cfg.csv \
             python scripts/sweep_l2.py --workloads citpatents --one $cfg > $O/ncu_l2_$cfg.log 2>&1
         note "l2ncu $cfg rc=$?"
       done ;;
+    sanitize_bulk) # compute-sanitizer over the bulk walker through the CLI
+      for tool in memcheck racecheck; do
+        echo "== $tool (GESPMM_VARIANT=5, K=128,200)" >> $O/sanitize_bulk.txt
+        GESPMM_VARIANT=5 timeout 300 compute-sanitizer --tool $tool --error-exitcode 9 ge-spmm_b200/bin/spmm_test $O/sanitize.mtx 0 \
+            --K 128,200 --iters 2 --validate --out $O/sanitize.csv 2>&1 | grep -E "SUMMARY|validate|WA|Error|error" | head -12 >> $O/sanitize_bulk.txt
+      done
+      note "sanitize_bulk done" ;;
     sanitize_rg) # compute-sanitizer over the row-group kernel (K = 3, 7, 13) through the CLI
       python - > $O/sanitize_gen.log 2>&1 <<'PY'
 import sys, numpy as np
@@ -93,6 +105,13 @@ PY
           rm -f /tmp/ncu_rg.ncu-rep
         done
       done ;;
+    multi)    # N GPUs (gpurun --gpus N): NCCL sharding test, then the bench line with its R-MAT record
+      NG=$(nvidia-smi -L | wc -l)
+      timeout 600 python -m pytest tests/test_sharding_nccl_gpu.py -x -q -m gpu > $O/t_nccl.log 2>&1; note "nccl test rc=$?"
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 \
+          bench.py --gpus $NG --steps 20 --warmup 5 > $O/bench_n$NG.json 2> $O/bench_n$NG.err; note "bench n=$NG rc=$?"
+      timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 \
+          bench.py --impl reference --gpus $NG --steps 20 --warmup 5 > $O/bench_n${NG}_reference.json 2> $O/bench_n${NG}_reference.err; note "bench reference n=$NG rc=$?" ;;
     rows)     # sub-warp (2) vs row-parallel (4) narrow walkers on every shape
       timeout 600 python scripts/sweep_narrow.py --variants 2,4 --tasks 0 > $O/sweep_v24.txt 2> $O/sweep_v24.err; note "rows rc=$?" ;;
     auto64)   # the SpMM suite with the sub-warp walker chosen automatically for K <= 64
