@@ -139,6 +139,18 @@ class ClockSampler(threading.Thread):
         return out
 
 
+def bind_near_gpu(index):
+    """One process per GPU: run this rank (and first-touch its pinned host buffers) on the CPUs NVML reports as nearest
+    to its GPU, so that the end-to-end copies do not cross the socket interconnect.  Returns the number of CPUs, or None."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(index))
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def physical_gpu_index(local_index):
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     if vis:
@@ -500,16 +512,19 @@ def rmat_record(args, R, dev, oracle, capi, spmm):
         return sh.forward(sh.all_gather_B_even(Bblk, out=Bfull))
 
     def step_pipe():
+        return sh.forward_replicating(Bblk, chunks=2)
+
+    def step_pipe4():
         return sh.forward_replicating(Bblk, chunks=4)
     repl = {}
-    for name, fn in (("allgather_then_product", step_seq), ("pipelined_4_panels", step_pipe)):
+    for name, fn in (("allgather_then_product", step_seq), ("pipelined_2_panels", step_pipe), ("pipelined_4_panels", step_pipe4)):
         for _ in range(2):
             Cp = fn()
         w2, m2, _ = timed_batches(fn, 5, 3, R)
         repl[name] = w2[m2]
     Cp = step_pipe()
     torch.cuda.synchronize()
-    par_pipe = merged_parity(R, check_parity(oracle, capi, sh.rowptr, sh.colind, sh.val, B, Cp, 32, seed=91 + rank))
+    par_pipe = merged_parity(R, check_parity(oracle, capi, sh.rowptr, sh.colind, sh.val, B, Cp, 64, seed=91 + rank))
     del Cp
     ms_1 = None
     if rank == 0:
@@ -580,6 +595,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_near_gpu(physical_gpu_index(local)) if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None
     R = Ranks(dev)
     rank, world, dist = R.rank, R.world, R.dist
     if world > 1:
@@ -723,7 +739,7 @@ def main():
         "clocks": clocks, "b_broadcast_ms": bcast_ms if world > 1 else None, "per_rank_ms": [round(x, 5) for x in per_rank_ms],
         "b_layout": ("row-sharded, remote rows gathered over NVLink inside the kernel (no replication); fraction of gathers "
                      "that are remote: %.3f" % remote_frac) if remote_frac is not None else "replicated on every rank",
-        "per_rank_rows_nnz": per_rank_shape, "per_rank_max_row_nnz": [int(x) for x in R.gather(sh.max_row_nnz)],
+        "per_rank_rows_nnz": per_rank_shape, "cpus_bound_near_gpu": numa, "per_rank_max_row_nnz": [int(x) for x in R.gather(sh.max_row_nnz)],
     }
 
     # reference kernel on the same GPU ("the bar on the B200 box"), whole matrix, rank 0 only

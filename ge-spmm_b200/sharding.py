@@ -145,14 +145,15 @@ class RowShardedSpMM:
         return _cuda_spmm(self.rowptr, self.colind, self.val, B_full, self.max_row_nnz)
 
     # -- replication overlapped with the product: column panels on a communication stream ----------------
-    def forward_replicating(self, B_block, chunks=4, sequential=False, out=None):
+    def forward_replicating(self, B_block, chunks=2, sequential=False, out=None):
         """C[row_lo:row_hi, :] = A[row block] @ B when B CHANGES EVERY STEP and arrives row-sharded in equal blocks
         (``even_b_block()`` rows per rank, zero-padded): the replication is not a separate phase.  The local block is
         re-laid out as ``chunks`` column panels; panel j is all-gathered over NVLink on a communication stream while the
         product of panel j - 1 (a [N, K / chunks] operand with row stride K / chunks, written into columns
         [j K / chunks, (j + 1) K / chunks) of C with row stride K -- the C ABI takes strides) runs on the caller's stream.
         One step then costs about max(all-gather, product) + one panel of the other instead of their sum.
-        K / chunks < 128 takes the narrow-B walkers: pass ``sequential=True`` for the bits of the plain product
+        Two panels of 64 columns are the default: the 64-column walker is as fast per column as the 128-column one, the
+        32-column one is not.  K / chunks < 128 takes the narrow-B walkers: pass ``sequential=True`` for the bits of the plain product
         (GESPMM_FLAG_SEQUENTIAL), else rows of more than one nonzero are re-associated (within ~2e-6 of max|C|)."""
         from . import capi
         blk, K = self.even_b_block(), B_block.shape[1]

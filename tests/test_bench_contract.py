@@ -47,7 +47,7 @@ def test_own_arm_needs_a_gpu():
 
 
 def test_committed_bench_line_carries_the_whole_contract():
-    """profiles/r01_bench_citpatents_n1.json is the own arm's line as printed on a B200 by the final kernels of round 1:
+    """profiles/r01_bench_citpatents_n1.json (round 1's line; round 2's: test_round2_bench_lines below) is the own arm's line as printed on a B200 by the final kernels of round 1:
     every key of the bench contract is there and the derived figures are consistent with each other."""
     with open(os.path.join(ROOT, "profiles", "r01_bench_citpatents_n1.json")) as f:
         d = json.loads(f.read())
@@ -72,3 +72,39 @@ def test_committed_bench_line_carries_the_whole_contract():
     assert d["vs_baseline"] == d["value"] / 140.4
     ref = d["reference_kernel_same_gpu"]
     assert ref["bitwise_equal_to_ours"] is True and ref["ms"] > d["ms_per_step"]
+
+
+def test_in_run_parity_check_accepts_the_oracle_and_catches_a_wrong_row(pkg, oracle):
+    """bench.check_parity (what every rank runs on its block of C before the line is printed): a C that IS the oracle's
+    result passes with every sampled row compared bit for bit; one flipped bit in one sampled row is reported."""
+    import numpy as np
+    import bench
+    from gespmm_b200 import capi, graphs
+    rp, ci = graphs.rmat(N=4000, nnz=60000, seed=3)
+    val = torch.rand(ci.numel(), generator=torch.Generator().manual_seed(1)) - 0.5
+    K = 128
+    B = graphs.cli_dense(4000, K, seed=2)
+    C = torch.from_numpy(oracle.spmm(rp.numpy(), ci.numpy(), val.numpy(), B.numpy(), fma=True))
+    p = bench.check_parity(oracle, capi, rp, ci, val, B, C, K, sample=500, seed=5)
+    assert p["rows_bad"] == 0 and p["rows_checked"] >= 400 and p["rows_bitwise"] == p["rows_checked"] and p["max_rel"] == 0.0
+    deg = (rp[1:] - rp[:-1])
+    hub = int(torch.argmax(deg))           # the longest row is always in the sample
+    C2 = C.clone()
+    C2[hub, 7] = float(np.nextafter(np.float32(C2[hub, 7]), np.float32(np.inf)))
+    assert bench.check_parity(oracle, capi, rp, ci, val, B, C2, K, sample=500, seed=5)["rows_bad"] == 1
+    # unvalued, and a width whose default walker re-associates (only rows of <= 1 nonzero are compared bit for bit)
+    Cu = torch.from_numpy(oracle.spmm(rp.numpy(), ci.numpy(), None, B[:, :32].contiguous().numpy()))
+    p = bench.check_parity(oracle, capi, rp, ci, None, B[:, :32].contiguous(), Cu, 32, sample=500, seed=5)
+    assert p["rows_bad"] == 0 and 0 < p["rows_bitwise"] < p["rows_checked"]
+
+
+def test_roofline_bytes_models():
+    import bench
+    assert bench.bytes_min(10, 20, 4, 30, valued=True) == 4 * 11 + 8 * 30 + 4 * 20 * 4 + 4 * 10 * 4
+    assert bench.bytes_min(10, 20, 4, 30, valued=False) == 4 * 11 + 4 * 30 + 4 * 20 * 4 + 4 * 10 * 4
+
+    class Shard:
+        row_lo, row_hi, nnz_local = 5, 15, 30
+    # a rank is charged for the B rows its block references, not for all of B
+    assert bench.rank_bytes(Shard, 4, True, distinct=7) == 4 * 11 + 8 * 30 + 4 * 4 * 7 + 4 * 10 * 4
+    assert bench.host_threads() >= 1
