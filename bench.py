@@ -56,7 +56,7 @@ WORKLOADS = {
     "rmat": "R-MAT(0.57,0.19,0.19,0.05) N=10000000 nnz=200000000 seed 4",
     "reddit": "Reddit shape-alike (N=232965, nnz=114615892) symmetric seed 2",
     "products": "ogbn-products shape-alike (N=2449029, nnz=123718280) symmetric seed 3",
-    "pubmed": "pubmed.mtx of the reference (tests/golden/pubmed_csr.npz)",
+    "pubmed": "PubMed shape-alike (N=19717, nnz=88648) symmetric seed 11",
 }
 
 
@@ -76,8 +76,7 @@ def make_graph(name, scale, device):
     if name == "products":
         return graphs.products_like(seed=3, device=device, scale=scale)
     if name == "pubmed":
-        z = np.load(os.path.join(ROOT, "tests", "golden", "pubmed_csr.npz"))
-        return torch.from_numpy(z["rowptr"]).to(device), torch.from_numpy(z["colind"]).to(device)
+        return graphs.social_like(19717, 88648, seed=11, device=device, sigma=1.0, locality=0.3, window=0.01)
     raise SystemExit("unknown workload %s" % name)
 
 
