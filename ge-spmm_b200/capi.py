@@ -35,7 +35,8 @@ class Opts(ctypes.Structure):
     _fields_ = [("struct_size", ctypes.c_uint32), ("flags", ctypes.c_uint32), ("max_row_nnz", ctypes.c_int64),
                 ("row_scale", ctypes.c_void_p), ("col_scale", ctypes.c_void_p), ("bias", ctypes.c_void_p),
                 ("walker", ctypes.c_int32), ("task_keys", ctypes.c_int32), ("long_row", ctypes.c_int32),
-                ("panel_v", ctypes.c_int32), ("l2_policy", ctypes.c_int32), ("l2_window_rows", ctypes.c_int32)]
+                ("panel_v", ctypes.c_int32), ("l2_policy", ctypes.c_int32), ("l2_window_rows", ctypes.c_int32),
+                ("hot_columns", ctypes.c_void_p)]
 
 
 class GespmmError(RuntimeError):
@@ -128,7 +129,7 @@ def csr_spmm_f32(M, N, K, nnz, rowptr, colind, val, B, ldb, C, ldc, stream=None)
 
 
 def opts(sequential=False, no_overlap=False, max_row_nnz=-1, row_scale=None, col_scale=None, bias=None, walker=0,
-         task_keys=0, long_row=0, panel_v=0, l2_policy=0, l2_window_rows=0):
+         task_keys=0, long_row=0, panel_v=0, l2_policy=0, l2_window_rows=0, hot_columns=None):
     """A gespmm_opts initialised by the library and filled in; the scale / bias arguments are device pointers (ints)."""
     o = Opts()
     lib().gespmm_opts_init(ctypes.byref(o))
@@ -137,6 +138,7 @@ def opts(sequential=False, no_overlap=False, max_row_nnz=-1, row_scale=None, col
     o.row_scale, o.col_scale, o.bias = row_scale or None, col_scale or None, bias or None
     o.walker, o.task_keys, o.long_row, o.panel_v = int(walker), int(task_keys), int(long_row), int(panel_v)
     o.l2_policy, o.l2_window_rows = int(l2_policy), int(l2_window_rows)
+    o.hot_columns = hot_columns or None
     return o
 
 

@@ -219,6 +219,7 @@ struct Operands {
     // L2 eviction-priority steering of the gathers (HINT walkers): priority code of "near" / "far" rows, the distance
     // |col - row| that separates them, and the priority of the C stores (codes: 0 normal, 1 evict_first, 2 evict_last, 3 unchanged)
     int l2_near, l2_far, l2_store, l2_window;
+    const unsigned *l2_hot;  // bit c set: column c is "hot" (one of the most referenced rows of B): always near
     PeerMap peer;
 };
 
@@ -718,6 +719,7 @@ struct WalkerBulk {
     unsigned long long pol_near, pol_far, pol_store;
     int window, cur_row;
     bool hint_store;
+    const unsigned *__restrict__ hot;
 
     __device__ __forceinline__ T start() const { return P::zero(); }
 
@@ -736,7 +738,7 @@ struct WalkerBulk {
         __syncwarp();
         if constexpr (HINT) {
             pol_near = l2_policy(o.l2_near); pol_far = l2_policy(o.l2_far); pol_store = l2_policy(o.l2_store);
-            window = o.l2_window; cur_row = 0; hint_store = o.l2_store != 0;
+            window = o.l2_window; cur_row = 0; hint_store = o.l2_store != 0; hot = o.l2_hot;
         }
     }
     __device__ __forceinline__ void finish(T (&)[1]) const {}
@@ -746,8 +748,12 @@ struct WalkerBulk {
     __device__ __forceinline__ int load_tok(int p) const {
         const int c = __ldcs(colind + p);
         if constexpr (HINT) {
+            // near = worth keeping in the L2: a hot column (the plan's bitmap of the most referenced rows of B), or a
+            // column within `window` rows of the rows being summed (banded graphs)
             const int d = c - cur_row;
-            return ((d < 0 ? -d : d) > window) ? (c | (int)0x80000000) : c;
+            bool near = (d < 0 ? -d : d) <= window;
+            if (hot) near = near || ((__ldg(hot + ((unsigned)c >> 5)) >> (c & 31)) & 1u);
+            return near ? c : (c | (int)0x80000000);
         } else {
             return c;
         }
@@ -1834,6 +1840,7 @@ struct Choice {
     bool overlap;
     long long max_row_nnz;
     const float *row_scale, *col_scale, *bias;
+    const unsigned *hot;
     bool fuse() const { return row_scale || col_scale || bias; }
 };
 Choice choose(const gespmm_opts *o)
@@ -1843,7 +1850,9 @@ Choice choose(const gespmm_opts *o)
     c.walker = t.walker; c.task = t.task; c.long_row = t.long_row; c.panel_v = t.panel_v; c.l2_policy = t.l2_policy;
     c.l2_window = t.l2_window; c.smem_pad = t.smem_pad; c.overlap = t.overlap != 0; c.max_row_nnz = -1;
     c.row_scale = c.col_scale = c.bias = nullptr;
+    c.hot = nullptr;
     if (o) {
+        c.hot = o->hot_columns;
         if (o->walker > 0) c.walker = o->walker;
         if (o->flags & GESPMM_FLAG_SEQUENTIAL) c.walker = GESPMM_WALKER_ROWS;
         if (o->flags & GESPMM_FLAG_NO_OVERLAP) c.overlap = false;
@@ -1852,6 +1861,7 @@ Choice choose(const gespmm_opts *o)
         if (o->panel_v > 0) c.panel_v = o->panel_v;
         if (o->l2_policy > 0) c.l2_policy = o->l2_policy;
         if (o->l2_window_rows > 0) c.l2_window = o->l2_window_rows;
+        else if (o->l2_window_rows < 0) c.l2_window = -1;  // no band: only hot columns count as near
         c.max_row_nnz = o->max_row_nnz;
         c.row_scale = o->row_scale; c.col_scale = o->col_scale; c.bias = o->bias;
     }
@@ -2083,6 +2093,7 @@ int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr
     a.op.row_scale = ch.row_scale; a.op.col_scale = ch.col_scale; a.op.bias = ch.bias;
     a.op.l2_near = ch.l2_policy & 3; a.op.l2_far = (ch.l2_policy >> 2) & 3; a.op.l2_store = (ch.l2_policy >> 4) & 3;
     a.op.l2_window = ch.l2_window;
+    a.op.l2_hot = ch.hot;
     const int mode = max_reduce ? 1 : (ch.fuse() ? 2 : 0);
     const bool hint = ch.l2_policy > 0 && mode == 0;
     const cudaError_t err = val ? dispatch_all<true>(mode, vec4, parts > 0, ch.walker, hint, V, masked, (int)K, a)

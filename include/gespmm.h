@@ -160,7 +160,10 @@ typedef struct gespmm_opts {
     int32_t  long_row;       /* long-row threshold override, [512, 2^20]                                         */
     int32_t  panel_v;        /* 128-column blocks per pass (1..4)                                                */
     int32_t  l2_policy;      /* experimental: L2 eviction-priority steering of the B gathers, see DESIGN.md 3.5  */
-    int32_t  l2_window_rows; /* experimental: |col - row| below which a gathered row counts as "near"            */
+    int32_t  l2_window_rows; /* experimental: |col - row| up to which a gathered row counts as "near" (0 = default
+                                131072, negative = no band at all)                                             */
+    const uint32_t *hot_columns; /* device bitmap, ceil(N / 32) words, bit c set = row c of B is among the most
+                                referenced ones ("hot": always near); NULL = none.  See gespmm_hot_columns.       */
 } gespmm_opts;
 
 void gespmm_opts_init(gespmm_opts *opts);

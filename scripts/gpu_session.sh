@@ -112,6 +112,14 @@ PY
           bench.py --gpus $NG --steps 20 --warmup 5 > $O/bench_n$NG.json 2> $O/bench_n$NG.err; note "bench n=$NG rc=$?"
       timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 \
           bench.py --impl reference --gpus $NG --steps 20 --warmup 5 > $O/bench_n${NG}_reference.json 2> $O/bench_n${NG}_reference.err; note "bench reference n=$NG rc=$?" ;;
+    hotsweep) # hot-column pinning in the L2 (bulk walker + gespmm_opts.hot_columns) on R-MAT 10M/200M
+      timeout 600 python scripts/sweep_hot.py > $O/sweep_hot.txt 2> $O/sweep_hot.err; note "hotsweep rc=$?"
+      for cfg in ${HOTNCU:-0,0,0 5,22,100000 5,22,150000}; do
+        timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct \
+            --clock-control none -k regex:spmm_flat --launch-skip 3 -c 1 --csv --log-file $O/ncu_hot_$cfg.csv \
+            python scripts/sweep_hot.py --one $cfg > $O/ncu_hot_$cfg.log 2>&1
+        note "hotncu $cfg rc=$?"
+      done ;;
     rows)     # sub-warp (2) vs row-parallel (4) narrow walkers on every shape
       timeout 600 python scripts/sweep_narrow.py --variants 2,4 --tasks 0 > $O/sweep_v24.txt 2> $O/sweep_v24.err; note "rows rc=$?" ;;
     auto64)   # the SpMM suite with the sub-warp walker chosen automatically for K <= 64
@@ -146,10 +154,13 @@ PY
       timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv \
           python bench.py --steps 3 --warmup 3 --no-cpu > $O/launches_bench.log 2>&1; note "launches rc=$?"
       python scripts/summarize_launches.py $O/launches.csv > $O/launches_summary.txt 2>&1 ;;
-    ncu128)   # one full capture of the dominant kernel of the bench command (cit-Patents shape, K = 128)
+    ncu128)   # one full capture of the dominant kernel of the bench command (cit-Patents shape, K = 128); exported as CSV pages
       timeout 400 ncu --set full --clock-control none --import-source on -k regex:spmm_flat_kernel --launch-skip 3 -c 1 \
-          -f -o $O/ncu_citpatents_K128 python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-ref-kernel > $O/ncu128.log 2>&1
-      note "ncu128 rc=$?" ;;
+          -f -o /tmp/ncu_citpatents_K128 python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-ref-kernel > $O/ncu128.log 2>&1
+      note "ncu128 rc=$?"
+      ncu -i /tmp/ncu_citpatents_K128.ncu-rep --page raw --csv > $O/ncu_citpatents_K128_raw.csv 2>/dev/null
+      ncu -i /tmp/ncu_citpatents_K128.ncu-rep --page source --csv > $O/ncu_citpatents_K128_source.csv 2>/dev/null
+      rm -f /tmp/ncu_citpatents_K128.ncu-rep ;;
     ncu)      # one full capture of each walker's kernel A on the ogbn-products shape, K = 32
       for v in 2 0; do
         GESPMM_VARIANT=$v timeout 400 ncu --set full --clock-control none --import-source on -k regex:spmm_flat_kernel --launch-skip 3 -c 1 \
