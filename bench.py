@@ -339,7 +339,8 @@ def timed_batches(step, steps, batches, R):
 
 def check_parity(oracle, capi, rowptr, colind, val, B, C, K, sample=1536, seed=0):
     """A sample of the rows of C (the longest few + random ones) against the oracle on the same inputs.
-    Bit for bit on the rows the library sums in CSR order (gespmm_row_sum_is_sequential), within
+    Bit for bit on the rows summed in CSR order (``capi.row_sum_is_sequential(K, row_nnz)``: the ctypes binding for bare
+    C ABI calls, the ``spmm`` extension module for products made through the operator), within
     1e-4 * max(|G|, sum |a||b|) of the fp64 golden on the others.  Returns a dict of counts (this rank)."""
     M = rowptr.numel() - 1
     if M == 0:
@@ -503,7 +504,7 @@ def rmat_record(args, R, dev, oracle, capi, spmm):
     ms_n = worst[mid]
     C = step()
     torch.cuda.synchronize()
-    par = merged_parity(R, check_parity(oracle, capi, sh.rowptr, sh.colind, sh.val, B, C, K, seed=17 + rank))
+    par = merged_parity(R, check_parity(oracle, spmm, sh.rowptr, sh.colind, sh.val, B, C, K, seed=17 + rank))
     del C
     # what one step costs when B changes every step: all-gather then product, vs the replication pipelined with the
     # product panel by panel (RowShardedSpMM.forward_replicating: 4 column panels on a communication stream)
@@ -523,7 +524,7 @@ def rmat_record(args, R, dev, oracle, capi, spmm):
         repl[name] = w2[m2]
     Cp = step_pipe()
     torch.cuda.synchronize()
-    par_pipe = merged_parity(R, check_parity(oracle, capi, sh.rowptr, sh.colind, sh.val, B, Cp, 64, seed=91 + rank))
+    par_pipe = merged_parity(R, check_parity(oracle, spmm, sh.rowptr, sh.colind, sh.val, B, Cp, 64, seed=91 + rank))
     del Cp
     ms_1 = None
     if rank == 0:
@@ -578,6 +579,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ref-kernel", action="store_true")
     ap.add_argument("--no-rmat", action="store_true", help="N > 1: skip the R-MAT 10M/200M record")
+    ap.add_argument("--no-uniform", action="store_true", help="N = 1: skip the uniformly-random variant of the cit-Patents shape")
     ap.add_argument("--rmat-scale", type=float, default=1.0)
     ap.add_argument("--b-sharded", action="store_true",
                     help="N > 1: leave B row-sharded (no replication) and let the kernel gather remote rows over NVLink")
@@ -665,7 +667,7 @@ def main():
     # parity: a sample of every rank's rows against the oracle; a mismatch fails the run
     C = step()
     torch.cuda.synchronize()
-    parity = merged_parity(R, check_parity(oracle, capi, sh.rowptr, sh.colind, sh.val, B, C, K, seed=rank))
+    parity = merged_parity(R, check_parity(oracle, spmm, sh.rowptr, sh.colind, sh.val, B, C, K, seed=rank))
 
     # roofline
     peak, peak_src = measured_peak_gbs()
@@ -768,6 +770,26 @@ def main():
             out["reference_kernel_same_gpu"] = {"unavailable": "oracle/_ref not built or int32 offsets would overflow"}
     if rank == 0 and not args.no_cpu and world == 1:  # rank 0 at N = 1 only
         out["cpu_baseline"] = cpu_legs(rowptr_full, colind_full, B, K)
+    if world == 1 and args.workload == "citpatents" and args.scale == 1.0 and not args.no_uniform:
+        # SURVEY.md 8d config 2 asks for the clustered AND the uniformly random graph: the same shape with every column
+        # drawn uniformly (no L2 reuse to find) next to the headline -- the floor for a kernel that does not reorder the graph
+        rp_u, ci_u = make_graph("citpatents_uniform", 1.0, dev)
+        v_u = torch.ones(ci_u.numel(), dtype=torch.float32, device=dev) if valued else None
+        mx_u = int(spmm.max_row_nnz(rp_u))
+
+        def step_u():
+            return spmm.csr_spmm_ex(rp_u, ci_u, v_u, B, max_row_nnz=mx_u)
+        for _ in range(3):
+            Cu = step_u()
+        w_u, m_u, _ = timed_batches(step_u, min(args.steps, 50), 3, R)
+        par_u = check_parity(oracle, spmm, rp_u, ci_u, v_u, B, Cu, K, sample=512, seed=3)
+        bm_u = float(bytes_min(M, N, K, ci_u.numel(), valued))
+        out["uniform_variant"] = {"workload": WORKLOADS["citpatents_uniform"], "ms_per_step": w_u[m_u],
+                                  "value": 2.0 * ci_u.numel() * K / w_u[m_u] / 1e6, "unit": "GFLOP/s",
+                                  "roofline_frac": bm_u / w_u[m_u] / 1e6 / peak, "rows_checked": par_u["rows_checked"],
+                                  "rows_bad": par_u["rows_bad"]}
+        parity["ok"] = parity["ok"] and par_u["rows_bad"] == 0
+        del rp_u, ci_u, v_u, Cu
 
     # BASELINE.json configs[4] (R-MAT 10M/200M, row-sharded) rides on the N > 1 line
     if world > 1 and not args.no_rmat:

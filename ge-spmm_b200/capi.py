@@ -19,7 +19,7 @@ LONG_ROW = 4096
 # every symbol include/gespmm.h declares
 SYMBOLS = (
     "gespmm_version", "gespmm_error_string", "gespmm_csr_spmm_f32", "gespmm_csr_spmm_f32_ex", "gespmm_opts_init", "gespmm_max_row_nnz",
-    "gespmm_reload_env", "gespmm_row_sum_is_sequential_ex", "gespmm_csr_spmm_f32_host", "gespmm_csr_spmm_f32_bparts", "gespmm_csr_spmm_max_f32", "gespmm_row_sum_is_sequential", "gespmm_enable_peer_access", "gespmm_ipc_open", "gespmm_ipc_close", "gespmm_ipc_alloc", "gespmm_ipc_free",
+    "gespmm_reload_env", "gespmm_thread_cleanup", "gespmm_pad_workspace_bytes", "gespmm_row_sum_is_sequential_ex", "gespmm_csr_spmm_f32_host", "gespmm_csr_spmm_f32_bparts", "gespmm_csr_spmm_max_f32", "gespmm_row_sum_is_sequential", "gespmm_enable_peer_access", "gespmm_ipc_open", "gespmm_ipc_close", "gespmm_ipc_alloc", "gespmm_ipc_free",
     "gespmm_csr2csc_workspace_bytes", "gespmm_csr2csc_f32", "gespmm_read_mtx", "gespmm_free_host",
     "gespmm_write_csr", "gespmm_read_csr", "gespmm_read_mtx_cached", "gespmm_write_mtx",
 )
@@ -36,7 +36,7 @@ class Opts(ctypes.Structure):
                 ("row_scale", ctypes.c_void_p), ("col_scale", ctypes.c_void_p), ("bias", ctypes.c_void_p),
                 ("walker", ctypes.c_int32), ("task_keys", ctypes.c_int32), ("long_row", ctypes.c_int32),
                 ("panel_v", ctypes.c_int32), ("l2_policy", ctypes.c_int32), ("l2_window_rows", ctypes.c_int32),
-                ("hot_columns", ctypes.c_void_p)]
+                ("hot_columns", ctypes.c_void_p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t)]
 
 
 class GespmmError(RuntimeError):
@@ -68,6 +68,10 @@ def lib():
         L.gespmm_max_row_nnz.argtypes = [i64, p, ctypes.POINTER(ctypes.c_int32), p]
         L.gespmm_reload_env.restype = None
         L.gespmm_reload_env.argtypes = []
+        L.gespmm_pad_workspace_bytes.restype = sz
+        L.gespmm_pad_workspace_bytes.argtypes = [i64, i64, i64]
+        L.gespmm_thread_cleanup.restype = None
+        L.gespmm_thread_cleanup.argtypes = []
         L.gespmm_row_sum_is_sequential_ex.restype = ctypes.c_int
         L.gespmm_row_sum_is_sequential_ex.argtypes = [i64, i64, ctypes.POINTER(Opts)]
         L.gespmm_csr_spmm_f32_bparts.restype = ctypes.c_int
@@ -129,7 +133,7 @@ def csr_spmm_f32(M, N, K, nnz, rowptr, colind, val, B, ldb, C, ldc, stream=None)
 
 
 def opts(sequential=False, no_overlap=False, max_row_nnz=-1, row_scale=None, col_scale=None, bias=None, walker=0,
-         task_keys=0, long_row=0, panel_v=0, l2_policy=0, l2_window_rows=0, hot_columns=None):
+         task_keys=0, long_row=0, panel_v=0, l2_policy=0, l2_window_rows=0, hot_columns=None, workspace=None, workspace_bytes=0):
     """A gespmm_opts initialised by the library and filled in; the scale / bias arguments are device pointers (ints)."""
     o = Opts()
     lib().gespmm_opts_init(ctypes.byref(o))
@@ -139,6 +143,7 @@ def opts(sequential=False, no_overlap=False, max_row_nnz=-1, row_scale=None, col
     o.walker, o.task_keys, o.long_row, o.panel_v = int(walker), int(task_keys), int(long_row), int(panel_v)
     o.l2_policy, o.l2_window_rows = int(l2_policy), int(l2_window_rows)
     o.hot_columns = hot_columns or None
+    o.workspace, o.workspace_bytes = workspace or None, int(workspace_bytes)
     return o
 
 
@@ -157,6 +162,16 @@ def max_row_nnz(M, rowptr, stream=None):
     if rc != OK:
         raise GespmmError(rc, "gespmm_max_row_nnz")
     return int(out.value)
+
+
+def pad_workspace_bytes(M, N, K):
+    """Bytes of Opts.workspace that let an odd width K > 16 run on the 16-byte-slice walkers (0: does not apply)."""
+    return int(lib().gespmm_pad_workspace_bytes(int(M), int(N), int(K)))
+
+
+def thread_cleanup():
+    """Release the calling thread's helper streams / events (they are re-created on demand)."""
+    lib().gespmm_thread_cleanup()
 
 
 def reload_env():

@@ -441,25 +441,29 @@ __device__ __forceinline__ float4 lds128(unsigned saddr)
 // FUSE: per-column scale on the gathered rows, per-row scale + bias on the stored rows (Operands).
 // HINT: every gather carries an L2 eviction priority chosen by the lane that loaded the column from the distance
 //       between the column and the rows being summed (bit 31 of the token = "far"); C stores carry one too.
+// W = floats per lane and pack: 4 (16-byte slices: K % 4 == 0, aligned operands) or 1 (4-byte slices: any K, any 4-byte
+//     alignment; cp.async.ca, the only 4-byte form) -- a pack is then 128 columns / 512 bytes or 32 columns / 128 bytes.
 template <int V, bool VALUED, int G, int NS, int CP, bool MASKED, bool PEER = false, bool MAXR = false, bool FUSE = false,
-          bool HINT = false>
+          bool HINT = false, int W = 4>
 struct WalkerRing {
-    using R = Reduce<Pack<true>, VALUED, MAXR, FUSE>;
-    using E = Epilogue<Pack<true>, FUSE>;
+    static_assert(W == 4 || (W == 1 && !PEER && !HINT), "4-byte slices: local B, no L2 hints");
+    using R = Reduce<Pack<W == 4>, VALUED, MAXR, FUSE>;
+    using E = Epilogue<Pack<W == 4>, FUSE>;
     static constexpr bool kFuse = FUSE;
     static_assert(!(HINT && PEER), "the L2 hints are for local B");
     float init_v;
-    __device__ __forceinline__ float4 start() const { return R::start(init_v); }
+    __device__ __forceinline__ typename Pack<W == 4>::T start() const { return R::start(init_v); }
     // what a lane keeps per prefetched nonzero: its column (B is one array) or the byte address of its
     // B row (B is a set of row blocks; the owner lookup is done once, by the lane that loaded the column)
     using Tok = typename std::conditional<PEER, unsigned long long, int>::type;
-    using P = Pack<true>;
-    using T = float4;
-    static constexpr int kStride = 128;
+    using P = Pack<W == 4>;
+    using T = typename P::T;
+    static constexpr int kStride = 32 * W;          // floats between a lane's consecutive packs
+    static constexpr int kPackBytes = 32 * 4 * W;   // one warp-wide copy: 512 or 128 bytes of a B row
     static constexpr int S32 = 32 / G;
     static constexpr int L = NS - 1;
     static constexpr int UB = G < 4 ? G : 4;  // rows read back from the ring per LDS batch
-    static constexpr int kStageBytes = G * V * 512;
+    static constexpr int kStageBytes = G * V * kPackBytes;
     static constexpr int kRingBytes = NS * kStageBytes;  // per warp
     static_assert(32 % G == 0 && S32 % NS == 0 && (NS & (NS - 1)) == 0 && L >= 1 && L <= S32 && G % UB == 0, "bad ring shape");
 
@@ -485,16 +489,16 @@ struct WalkerRing {
     int window, cur_row;
     bool hint_store;            // store priority 0 = the plain streaming store
 
-    static constexpr int kPanel = 128 * V;
+    static constexpr int kPanel = kStride * V;
     __device__ __forceinline__ void init(const Operands &o, int panel, int K, int ln, unsigned ring_base) {
-        const int col0 = panel * kPanel + ln * 4;
+        const int col0 = panel * kPanel + ln * W;
         vmask = 0;
 #pragma unroll
         for (int v = 0; v < V; v++)
             if (col0 + v * kStride < K) vmask |= 1u << v;
         colind = o.colind; val = o.val; Bl = reinterpret_cast<const char *>(o.B + col0); Cl = o.C + col0;
         ldb_bytes = (unsigned)o.ldb * 4u; ldc = o.ldc; lane = ln;
-        ring = ring_base + ln * 16;
+        ring = ring_base + ln * (4 * W);
         peer = &o.peer; lane_off = (unsigned)col0 * 4u;
         init_v = o.init;
         if constexpr (FUSE) {
@@ -545,7 +549,7 @@ struct WalkerRing {
         for (int v = 0; v < V; v++) {
             if (pack_on(v)) {
                 const T out = FUSE ? E::apply(acc[v], rs, bias_v[v], has_bias) : acc[v];
-                if constexpr (HINT) {
+                if constexpr (HINT && W == 4) {
                     if (hint_store) st_hint_f4(c + v * kStride, out, pol_store);
                     else P::stcs(c + v * kStride, out);
                 } else P::stcs(c + v * kStride, out);
@@ -577,7 +581,8 @@ struct WalkerRing {
                             // (cp.async with an L2 cache-hint operand assembles -- LDGSTS with a policy descriptor -- but
                             // traps as an illegal instruction on sm_100a, profiles/r02_ldgsts_cache_hint_illegal_instruction.txt:
                             // per-gather priorities are the bulk walker's business)
-                            cp_async16<CP>(ring + slot + ((i0 + i) * V + v) * 512, bp[i] + v * 512);
+                            if constexpr (W == 4) cp_async16<CP>(ring + slot + ((i0 + i) * V + v) * kPackBytes, bp[i] + v * kPackBytes);
+                            else cp_async4(ring + slot + ((i0 + i) * V + v) * kPackBytes, bp[i] + v * kPackBytes);
                         }
                     }
                 }
@@ -612,7 +617,10 @@ struct WalkerRing {
                 if (FULL || pos0 + i0 + i < n) {
 #pragma unroll
                     for (int v = 0; v < V; v++)
-                        if (pack_on(v)) b[i][v] = lds128(ring + slot + ((i0 + i) * V + v) * 512);
+                        if (pack_on(v)) {
+                            if constexpr (W == 4) b[i][v] = lds128(ring + slot + ((i0 + i) * V + v) * kPackBytes);
+                            else b[i][v] = lds32(ring + slot + ((i0 + i) * V + v) * kPackBytes);
+                        }
                 }
             }
             const unsigned ends = (endmask >> (pos0 + i0)) & ((1u << UB) - 1u);
@@ -1668,9 +1676,15 @@ struct Side {
 };
 constexpr int kMaxDevices = 64;
 
-Side *side_for_current_device()
+Side *thread_sides()
 {
     thread_local Side sides[kMaxDevices];
+    return sides;
+}
+
+Side *side_for_current_device()
+{
+    Side *sides = thread_sides();
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
     Side &sd = sides[dev];
@@ -1841,6 +1855,8 @@ struct Choice {
     long long max_row_nnz;
     const float *row_scale, *col_scale, *bias;
     const unsigned *hot;
+    void *workspace;
+    size_t workspace_bytes;
     bool fuse() const { return row_scale || col_scale || bias; }
 };
 Choice choose(const gespmm_opts *o)
@@ -1851,8 +1867,10 @@ Choice choose(const gespmm_opts *o)
     c.l2_window = t.l2_window; c.smem_pad = t.smem_pad; c.overlap = t.overlap != 0; c.max_row_nnz = -1;
     c.row_scale = c.col_scale = c.bias = nullptr;
     c.hot = nullptr;
+    c.workspace = nullptr; c.workspace_bytes = 0;
     if (o) {
         c.hot = o->hot_columns;
+        c.workspace = o->workspace; c.workspace_bytes = o->workspace_bytes;
         if (o->walker > 0) c.walker = o->walker;
         if (o->flags & GESPMM_FLAG_SEQUENTIAL) c.walker = GESPMM_WALKER_ROWS;
         if (o->flags & GESPMM_FLAG_NO_OVERLAP) c.overlap = false;
@@ -1928,7 +1946,26 @@ cudaError_t dispatch_rows(int K, const Args &a)
     return launch<WalkerRows<8, VALUED, MAXR, FUSE>, 1, true, 24, WalkerSub<8, VALUED, MAXR, FUSE>>(a);
 }
 
-// Scalar instantiations of the register walker: any K, any alignment.
+// Any K, any 4-byte alignment, above the lane-group walkers' K <= 16: the ring walker on 4-byte slices -- 32 columns per
+// pack, up to 4 packs per lane (128-column panels), 16 (V <= 2) or 8 rows per stage.
+template <int V, bool VALUED, bool MAXR, bool FUSE>
+cudaError_t launch_ring1(const Args &a)
+{
+    constexpr int G = V <= 2 ? 16 : 8;  // 4-8 KB of ring per warp either way
+    return launch<WalkerRing<V, VALUED, G, 2, 0, true, false, MAXR, FUSE, false, 1>, V, false, 24>(a);
+}
+template <bool VALUED, bool MAXR, bool FUSE>
+cudaError_t dispatch_ring1(int V, const Args &a)
+{
+    switch (V) {
+        case 1: return launch_ring1<1, VALUED, MAXR, FUSE>(a);
+        case 2: return launch_ring1<2, VALUED, MAXR, FUSE>(a);
+        case 3: return launch_ring1<3, VALUED, MAXR, FUSE>(a);
+        default: return launch_ring1<4, VALUED, MAXR, FUSE>(a);
+    }
+}
+
+// Scalar instantiations of the register walker: any K, any alignment (GESPMM_WALKER_REGISTER; comparisons).
 template <bool VALUED, bool MAXR, bool FUSE>
 cudaError_t dispatch_scalar(int V, const Args &a)
 {
@@ -1969,6 +2006,11 @@ cudaError_t dispatch_all(int mode, bool vec4, bool peer, int walker, bool hint, 
         if (mode == 2) return dispatch_sub1<VALUED, false, true>(K, a);
         return dispatch_sub1<VALUED, false, false>(K, a);
     }
+    if (!vec4 && walker != GESPMM_WALKER_REGISTER) {
+        if (mode == 1) return dispatch_ring1<VALUED, true, false>(V, a);
+        if (mode == 2) return dispatch_ring1<VALUED, false, true>(V, a);
+        return dispatch_ring1<VALUED, false, false>(V, a);
+    }
     if (!vec4) {
         if (mode == 1) return dispatch_scalar<VALUED, true, false>(V, a);
         if (mode == 2) return dispatch_scalar<VALUED, false, true>(V, a);
@@ -1996,6 +2038,32 @@ cudaError_t dispatch_all(int mode, bool vec4, bool peer, int walker, bool hint, 
     return dispatch_ring<VALUED, false, false>(V, a, masked);
 }
 
+// Row padding for widths that are not multiples of 4 (gespmm_opts.workspace): dst[r, 0:K4) = src[r, 0:K) followed by zeros,
+// one float4 store per thread; and the way back, dst[r, 0:K) = src[r, 0:K) of a K4-strided source.
+__global__ void pad_rows_kernel(long long rows, int K, int K4, const float *__restrict__ src, long long lds, float *__restrict__ dst)
+{
+    const int q4 = K4 >> 2;
+    const long long total = rows * q4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / q4;
+        const int c = (int)(i - r * q4) << 2;
+        const float *s = src + r * lds + c;
+        float4 v;
+        v.x = c + 0 < K ? __ldg(s + 0) : 0.f; v.y = c + 1 < K ? __ldg(s + 1) : 0.f;
+        v.z = c + 2 < K ? __ldg(s + 2) : 0.f; v.w = c + 3 < K ? __ldg(s + 3) : 0.f;
+        reinterpret_cast<float4 *>(dst)[i] = v;
+    }
+}
+__global__ void unpad_rows_kernel(long long rows, int K, int K4, const float *__restrict__ src, float *__restrict__ dst, long long ldd)
+{
+    const long long total = rows * K;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / K;
+        const int c = (int)(i - r * K);
+        __stcs(dst + r * ldd + c, __ldcs(src + r * K4 + c));
+    }
+}
+
 __global__ void max_row_kernel(int M, const int *__restrict__ rowptr, int *__restrict__ out)
 {
     int best = 0;
@@ -2008,6 +2076,13 @@ __global__ void max_row_kernel(int M, const int *__restrict__ rowptr, int *__res
 }  // namespace
 
 namespace {
+
+size_t align64(size_t floats) { return (floats + 63) & ~(size_t)63; }  // 256-byte aligned sub-buffers
+size_t pad_workspace_bytes(int64_t M, int64_t N, int64_t K)
+{
+    const size_t K4 = (size_t)((K + 3) & ~3LL);
+    return (align64((size_t)N * K4) + align64((size_t)M * K4) + align64(K4)) * sizeof(float);
+}
 
 // Shared by the entry points: argument checks, task window, dispatch.  `parts` == 0: B is one array.
 int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr, const int32_t *colind, const float *val,
@@ -2047,6 +2122,34 @@ int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr
         if (!vec4) return GESPMM_ERR_INVALID_ARG;  // needs K % 4 == 0 and 16-byte aligned, 4-float-strided operands
     } else {
         vec4 = vec4 && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+    }
+    // A width that is not a multiple of 4, above the lane-group walkers' K <= 16, with a caller-given workspace: B is
+    // copied into rows padded to K4 = 4 ceil(K / 4) floats, the product runs on the 16-byte-slice walkers IN SEQUENTIAL
+    // ORDER (so the bits are those of the unpadded path and of the reference, whichever path a graph takes), and C comes
+    // back through the same padding.  The 4-byte-slice ring walker is instruction-bound (ogbn-products shape, K = 41 / 47:
+    // 5.5 / 5.8 ms against 3.1 / 2.7 padded); the two extra passes over B and C cost about as much as 2.5 nonzeros per row
+    // of B and C, so graphs sparser than 4 nonzeros per (row of B + row of C) stay unpadded (cit-Patents shape: 0.98 vs 1.27).
+    if (parts == 0 && K % 4 != 0 && K > kRowGroupMaxK && ch.workspace && ch.walker != GESPMM_WALKER_REGISTER &&
+        nnz >= 4 * (M + N)) {
+        const int64_t K4 = (K + 3) & ~3LL;
+        const size_t need = pad_workspace_bytes(M, N, K);
+        if (ch.workspace_bytes < need || (reinterpret_cast<uintptr_t>(ch.workspace) & 255)) return GESPMM_ERR_WORKSPACE;
+        float *Bp = static_cast<float *>(ch.workspace);
+        float *Cp = Bp + align64((size_t)N * K4);
+        float *biasp = Cp + align64((size_t)M * K4);
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const int blocks = 148 * 8;
+        if (nnz > 0) pad_rows_kernel<<<blocks, 256, 0, st>>>(N, (int)K, (int)K4, B, ldb, Bp);
+        if (ch.bias) pad_rows_kernel<<<1, 64, 0, st>>>(1, (int)K, (int)K4, ch.bias, K, biasp);
+        gespmm_opts inner;
+        if (opts) inner = *opts; else gespmm_opts_init(&inner);
+        inner.workspace = nullptr; inner.workspace_bytes = 0;
+        inner.flags |= GESPMM_FLAG_SEQUENTIAL;
+        if (ch.bias) inner.bias = biasp;
+        const int rc = run_spmm(M, N, K4, nnz, rowptr, colind, val, Bp, 0, nullptr, nullptr, K4, Cp, K4, stream, &inner, max_reduce, init);
+        if (rc != GESPMM_OK) return rc;
+        unpad_rows_kernel<<<blocks, 256, 0, st>>>(M, (int)K, (int)K4, Cp, C, ldc);
+        return cudaGetLastError() == cudaSuccess ? GESPMM_OK : GESPMM_ERR_CUDA;
     }
     const int W = vec4 ? 4 : 1;
     const int packs = (int)((K + 32 * W - 1) / (32 * W));
@@ -2104,6 +2207,7 @@ int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr
 int sequential_for(int64_t K, int64_t row_nnz, const Choice &ch)
 {
     if (row_nnz > ch.long_row) return 0;  // segmented (kernel B)
+    // (a width that is not a multiple of 4 above 16 is summed in CSR order with or without a padding workspace)
     if (row_nnz > 1 && use_subwarp(K, ch.walker) && !use_rows(K, ch.walker)) return 0;  // per-group partial sums
     // widths that are not multiples of 4 up to 16: the same sub-warp walker on 4-byte slices unless a sequential
     // walker was asked for (row-group kernel / register walker)
@@ -2114,12 +2218,38 @@ int sequential_for(int64_t K, int64_t row_nnz, const Choice &ch)
 
 }  // namespace
 
+extern "C" size_t gespmm_pad_workspace_bytes(int64_t M, int64_t N, int64_t K)
+{
+    if (M < 0 || N < 0 || K <= kRowGroupMaxK || K % 4 == 0) return 0;
+    return pad_workspace_bytes(M, N, K);
+}
+
 extern "C" void gespmm_opts_init(gespmm_opts *opts)
 {
     if (!opts) return;
     memset(opts, 0, sizeof(*opts));
     opts->struct_size = (uint32_t)sizeof(*opts);
     opts->max_row_nnz = -1;
+}
+
+extern "C" void gespmm_thread_cleanup(void)
+{
+    Side *sides = thread_sides();
+    int cur = 0;
+    const bool have_cur = cudaGetDevice(&cur) == cudaSuccess;
+    for (int d = 0; d < kMaxDevices; d++) {
+        Side &sd = sides[d];
+        if (!sd.ok) continue;
+        if (cudaSetDevice(d) == cudaSuccess) {
+            cudaStreamSynchronize(sd.stream);
+            cudaEventDestroy(sd.join);
+            cudaEventDestroy(sd.fork);
+            cudaStreamDestroy(sd.stream);
+        }
+        sd = Side();
+    }
+    if (have_cur) cudaSetDevice(cur);
+    cudaGetLastError();
 }
 
 extern "C" void gespmm_reload_env(void)

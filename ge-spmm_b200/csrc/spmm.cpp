@@ -43,6 +43,18 @@ torch::Tensor run(const torch::Tensor &rowptr, const torch::Tensor &colind, cons
     c10::cuda::CUDAGuard guard(B.device());
     auto out = torch::empty({M, K}, B.options());  // spmm_kernel.cu:182-184
     cudaStream_t stream = at::cuda::getCurrentCUDAStream();
+    // widths that are not multiples of 4 (K > 16): the library runs them on its 16-byte-slice walkers through padded
+    // copies of B and C when it is handed scratch memory; the caching allocator makes that free after the first call
+    gespmm_opts with_ws;
+    torch::Tensor ws;
+    const size_t ws_bytes = gespmm_pad_workspace_bytes(M, N, K);
+    if (ws_bytes > 0) {
+        if (opts) with_ws = *opts; else gespmm_opts_init(&with_ws);
+        ws = torch::empty({(int64_t)ws_bytes}, B.options().dtype(torch::kUInt8));
+        with_ws.workspace = ws.data_ptr();
+        with_ws.workspace_bytes = ws_bytes;
+        opts = &with_ws;
+    }
     const int rc = gespmm_csr_spmm_f32_ex(M, N, K, nnz, rowptr.data_ptr<int>(), colind.data_ptr<int>(), val,
                                           B.data_ptr<float>(), K, out.data_ptr<float>(), K, opts, stream);
     TORCH_CHECK(rc == GESPMM_OK, "gespmm_csr_spmm_f32 failed: ", gespmm_error_string(rc));
@@ -133,6 +145,16 @@ torch::Tensor csr_spmm_ex(torch::Tensor A_rowptr, torch::Tensor A_colind, c10::o
     return run(A_rowptr, A_colind, val, B, &o);
 }
 
+// Whether this operator sums a row of `row_nnz` nonzeros at width K in the reference's sequential order
+// (gespmm_row_sum_is_sequential_ex for the options csr_spmm / csr_spmm_ex pass).
+bool row_sum_is_sequential(int64_t K, int64_t row_nnz, bool sequential)
+{
+    gespmm_opts o;
+    gespmm_opts_init(&o);
+    if (sequential) o.flags |= GESPMM_FLAG_SEQUENTIAL;
+    return gespmm_row_sum_is_sequential_ex(K, row_nnz, &o) != 0;
+}
+
 // Longest row of a CSR on the device (one small kernel + a 4-byte copy back; synchronises the current stream).
 int64_t max_row_nnz(torch::Tensor rowptr)
 {
@@ -156,4 +178,6 @@ PYBIND11_MODULE(spmm, m)
           pybind11::arg("sequential") = false, pybind11::arg("max_row_nnz") = -1, pybind11::arg("row_scale") = pybind11::none(),
           pybind11::arg("col_scale") = pybind11::none(), pybind11::arg("bias") = pybind11::none());
     m.def("max_row_nnz", &max_row_nnz, "longest row of a device CSR");
+    m.def("row_sum_is_sequential", &row_sum_is_sequential, "does this operator sum such a row in CSR order (bit-identical to the reference)?",
+          pybind11::arg("K"), pybind11::arg("row_nnz"), pybind11::arg("sequential") = false);
 }

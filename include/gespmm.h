@@ -162,9 +162,18 @@ typedef struct gespmm_opts {
     int32_t  l2_policy;      /* experimental: L2 eviction-priority steering of the B gathers, see DESIGN.md 3.5  */
     int32_t  l2_window_rows; /* experimental: |col - row| up to which a gathered row counts as "near" (0 = default
                                 131072, negative = no band at all)                                             */
-    const uint32_t *hot_columns; /* device bitmap, ceil(N / 32) words, bit c set = row c of B is among the most
-                                referenced ones ("hot": always near); NULL = none.  See gespmm_hot_columns.       */
+    const uint32_t *hot_columns; /* experimental: device bitmap, ceil(N / 32) words, bit c set = row c of B is among
+                                the most referenced ones ("hot": always near); NULL = none           */
+    void    *workspace;      /* optional device scratch, 256-byte aligned, of at least                            */
+    size_t   workspace_bytes;/* gespmm_pad_workspace_bytes(M, N, K) bytes: lets a width that is not a multiple of 4
+                                (K > 16) run on the 16-byte-slice walkers through padded copies of B and C when the graph
+                                is dense enough for that to pay (nnz >= 4 (M + N)): ~2x the 4-byte-slice path at K = 41,
+                                47.  Same bits either way (sequential order).  Without it nothing is padded.            */
 } gespmm_opts;
+
+/* Bytes of gespmm_opts.workspace that the padded path needs for this product; 0 when it does not apply
+ * (K % 4 == 0 or K <= 16). */
+size_t gespmm_pad_workspace_bytes(int64_t M, int64_t N, int64_t K);
 
 void gespmm_opts_init(gespmm_opts *opts);
 
@@ -188,6 +197,13 @@ int gespmm_max_row_nnz(int64_t M, const int32_t *rowptr, int32_t *out_host, void
  * scripts and tests that change the environment of a running process; not thread-safe against concurrent calls).
  */
 void gespmm_reload_env(void);
+
+/*
+ * The library's only hidden state is one helper stream + two events per (host thread, device), created on the first
+ * product of a matrix that may hold long rows (conventions above).  A host thread that is about to exit -- or a host
+ * that wants the device reset cleanly -- releases its own with this call; the next product re-creates them.
+ */
+void gespmm_thread_cleanup(void);
 
 /* gespmm_row_sum_is_sequential for a call made with `opts` (NULL: same as the plain function). */
 int gespmm_row_sum_is_sequential_ex(int64_t K, int64_t row_nnz, const gespmm_opts *opts);

@@ -127,6 +127,9 @@ PY
     bench)
       timeout 600 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; note "bench rc=$?"
       timeout 300 python bench.py --impl reference > $O/bench_n1_reference.json 2> $O/bench_n1_reference.err; note "bench reference rc=$?" ;;
+    benchdrv) # the driver's own invocation at N = 1
+      timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > $O/bench_n1_drv.json 2> $O/bench_n1_drv.err; note "benchdrv rc=$?"
+      timeout 300 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > $O/bench_n1_drv_reference.json 2> $O/bench_n1_drv_reference.err; note "benchdrv reference rc=$?" ;;
     smoke)
       timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; note "smoke rc=$?" ;;
     sanitize) # compute-sanitizer over the sub-warp kernels through the CLI

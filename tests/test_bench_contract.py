@@ -108,3 +108,38 @@ def test_roofline_bytes_models():
     # a rank is charged for the B rows its block references, not for all of B
     assert bench.rank_bytes(Shard, 4, True, distinct=7) == 4 * 11 + 8 * 30 + 4 * 4 * 7 + 4 * 10 * 4
     assert bench.host_threads() >= 1
+
+
+def test_round2_bench_lines():
+    """profiles/r02_bench_n{1,2,4,8}_builder*.json: the own arm's lines as printed on B200s by the final code of round 2
+    (builder runs; the driver's own runs are BENCH_r02 / SCALE_r02).  What round 1's verdict asked of them: parity checked
+    inside the run at every N, the R-MAT 10M/200M record with its speed-up on the N > 1 lines, a roofline fraction that stays
+    below 1, host-to-device bytes that do not grow with N, the uniformly random variant beside the N = 1 headline."""
+    lines = {}
+    for n, name in ((1, "r02_bench_n1_builder.json"), (2, "r02_bench_n2_builder.json"), (4, "r02_bench_n4_builder.json"),
+                    (8, "r02_bench_n8_builder.json")):
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            lines[n] = json.loads(f.read())
+    for n, d in lines.items():
+        assert BASE_KEYS <= set(d) and d["n_gpus"] == n and d["metric"] == "spmm_gflops"
+        assert d["parity"]["ok"] is True and d["parity"]["rows_bad"] == 0 and d["parity"]["rows_checked"] >= 1500 * n
+        assert d["parity"]["rows_bitwise_vs_oracle"] == d["parity"]["rows_checked"]          # K = 128: every sampled row bit for bit
+        assert len(d["batches_ms_per_step"]) == 5 and min(d["batches_ms_per_step"]) <= d["ms_per_step"] <= max(d["batches_ms_per_step"])
+        r = d["roofline"]
+        assert r["bound"] == "hbm" and 0.3 < r["frac"] < 1.0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert (r["traffic"] is None) == (n > 1)                                              # ncu bytes only where they were measured
+        assert d["gpu_launches_per_step"] == 1                                                # no long rows: the long-row kernel is skipped
+        e = d["e2e"]
+        assert 2.0e9 < e["h2d_bytes_per_step"] < 2.2e9 and e["d2h_bytes_per_step"] == 4 * d["config"]["M"] * d["config"]["K"]
+        assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])
+    assert lines[1]["e2e"]["value"] < lines[2]["e2e"]["value"] and lines[1]["e2e"]["value"] < lines[8]["e2e"]["value"]
+    assert lines[1]["value"] < lines[2]["value"] < lines[4]["value"] < lines[8]["value"]
+    assert "uniform_variant" in lines[1] and lines[1]["uniform_variant"]["rows_bad"] == 0
+    assert lines[1]["uniform_variant"]["roofline_frac"] < lines[1]["roofline"]["frac"]
+    for n in (2, 4, 8):
+        m = lines[n]["rmat"]
+        assert m["n_gpus"] == n and m["parity"]["ok"] and m["parity"]["rows_bad"] == 0 and m["b_replicas_identical"]
+        assert abs(m["speedup"] - m["ms_1gpu"] / m["ms_per_step"]) < 1e-9 and m["roofline"]["frac"] < 1.0
+        assert m["b_allgather_ms"] < m["b_broadcast_ms"]
+    assert lines[4]["rmat"]["speedup"] >= 3.5                                                 # BASELINE.json north_star
+    assert lines[2]["rmat"]["speedup"] > 1.8 and lines[8]["rmat"]["speedup"] > 6.5

@@ -308,8 +308,13 @@ def test_mtx_writer_roundtrip(pkg, tmp_path, golden_csr):
 def test_operator_module_surface(pkg):
     from gespmm_b200 import op
     names = sorted(n for n in dir(op.spmm) if not n.startswith("_"))
-    assert [n for n in names if n not in ("csr_spmm_ex", "max_row_nnz")] == ["csr2csc", "csr_spmm", "csr_spmm_no_edge_value"]  # spmm.cpp:96-101
-    assert "csr_spmm_ex" in names and "max_row_nnz" in names  # the additions: per-call options, fused scaling
+    extra = ("csr_spmm_ex", "max_row_nnz", "row_sum_is_sequential")   # the additions: per-call options, fused scaling, order query
+    assert [n for n in names if n not in extra] == ["csr2csc", "csr_spmm", "csr_spmm_no_edge_value"]  # spmm.cpp:96-101
+    assert all(n in names for n in extra)
+    assert op.spmm.row_sum_is_sequential(128, 4096) and not op.spmm.row_sum_is_sequential(128, 4097)
+    assert not op.spmm.row_sum_is_sequential(32, 2) and op.spmm.row_sum_is_sequential(32, 2, True)
+    assert op.spmm.row_sum_is_sequential(41, 2) and op.spmm.row_sum_is_sequential(127, 2)   # odd widths above 16: always CSR order
+    assert not op.spmm.row_sum_is_sequential(7, 2) and op.spmm.row_sum_is_sequential(7, 2, True)
     assert op.spmm.__doc__.startswith("spmm in CSR format")  # spmm.cpp:97
     rp = torch.zeros(5, dtype=torch.int32); ci = torch.zeros(0, dtype=torch.int32); B = torch.zeros(4, 8)
     with pytest.raises(RuntimeError, match="CUDA"):  # reference: C assert -> abort; here: exception, and no CPU path

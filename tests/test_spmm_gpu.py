@@ -61,13 +61,14 @@ def _run(spmm, dev, rowptr, colind, val, B):
 
 
 def _sequential_rows(rowptr, K):
-    """Rows the library sums in the reference's order (include/gespmm.h: gespmm_row_sum_is_sequential)."""
-    from gespmm_b200 import capi
+    """Rows the OPERATOR sums in the reference's order (spmm.row_sum_is_sequential: gespmm_row_sum_is_sequential_ex for
+    the options the extension passes -- it hands the library a padding workspace for widths that are not multiples of 4)."""
+    from gespmm_b200.op import spmm as q
     deg = np.diff(rowptr)
-    assert capi.row_sum_is_sequential(K, 1) and capi.row_sum_is_sequential(K, 0)
-    assert not capi.row_sum_is_sequential(K, LONG + 1)
-    if capi.row_sum_is_sequential(K, 2):
-        assert capi.row_sum_is_sequential(K, LONG)
+    assert q.row_sum_is_sequential(K, 1) and q.row_sum_is_sequential(K, 0)
+    assert not q.row_sum_is_sequential(K, LONG + 1)
+    if q.row_sum_is_sequential(K, 2):
+        assert q.row_sum_is_sequential(K, LONG)
         return deg <= LONG
     return deg <= 1
 
@@ -84,6 +85,17 @@ def _check(oracle, rowptr, colind, val, B, C):
         err = np.abs(C.astype(np.float64) - G)
         assert (err <= RTOL * np.maximum(np.abs(G), mag) + 1e-30).all()
     return int((np.diff(rowptr) > LONG).sum())
+
+
+def _check_with(oracle, rowptr, colind, val, B, C, sequential):
+    """_check for a call whose summation order the caller states itself (C ABI calls with their own options)."""
+    C = C.cpu().numpy()
+    want = oracle.spmm(rowptr, colind, val, B, fma=True)
+    deg = np.diff(rowptr)
+    seq = (deg <= LONG) if sequential else (deg <= 1)
+    assert np.array_equal(C[seq], want[seq])
+    G, mag = oracle.spmm_f64(rowptr, colind, val, B)
+    assert (np.abs(C.astype(np.float64) - G) <= RTOL * np.maximum(np.abs(G), mag) + 1e-30).all()
 
 
 def _rand_csr(rng, M, N, nnz, empty_frac=0.0):
@@ -228,7 +240,8 @@ def test_subwarp_walker_for_narrow_B(spmm, dev, oracle, pkg, gespmm_env, K):
     # not a multiple of 4: up to K = 16 the same walker runs on 4-byte slices (re-associated, within tolerance; exact on
     # integer-valued operands), above that the sequential scalar walker (bit-identical)
     B3 = rng.standard_normal((N, K - 1)).astype(np.float32)
-    assert capi.row_sum_is_sequential(K - 1, 2) == (K - 1 > 16)
+    assert capi.row_sum_is_sequential(K - 1, 2) == (K - 1 > 16) == spmm.row_sum_is_sequential(K - 1, 2)
+    assert spmm.row_sum_is_sequential(K - 1, LONG, True)
     for v in (None, vf):
         _check(oracle, rowptr, colind, v, B3, _run(spmm, dev, rowptr, colind, v, B3))
     B3i = rng.integers(-8, 9, (N, K - 1)).astype(np.float32)
@@ -333,12 +346,73 @@ def test_fused_scales_and_bias_match_the_separate_passes_bitwise(spmm, dev, orac
                     y = y + bd
                 torch.cuda.synchronize()
                 assert torch.equal(got, y), "fused != separate passes (K=%d sequential=%s valued=%s use=%s)" % (K, sequential, v is not None, use)
-        from gespmm_b200 import capi
-        if capi.row_sum_is_sequential(K, 2, capi.opts(sequential=sequential)):   # against the oracle, on the rows summed in CSR order
+        if spmm.row_sum_is_sequential(K, 2, sequential):   # against the oracle, on the rows summed in CSR order
             xs = (Bf * cs[:, None]).astype(np.float32)
             want = (oracle.spmm(rowptr, colind, vf, xs, fma=True) * rs[:, None]).astype(np.float32) + bias
             got = spmm.csr_spmm_ex(rp, ci, vd, Bd, sequential=sequential, row_scale=rsd, col_scale=csd, bias=bd).cpu().numpy()
             assert np.array_equal(got[short], want[short])
+
+
+@pytest.mark.parametrize("K", [17, 31, 41, 47, 63, 65, 127, 130])
+def test_widths_that_are_not_multiples_of_4_padded_and_unpadded(spmm, dev, oracle, pkg, K):
+    """K % 4 != 0 above 16.  Bare C ABI call: the ring walker on 4-byte slices, sequential order, bit-identical to the oracle.
+    With gespmm_opts.workspace (what the operator always passes) and a graph dense enough (this one: nnz / (M + N) = 15):
+    padded copies of B and C, the 16-byte-slice walkers in sequential order -- the same bits; a sparser graph stays
+    unpadded -- the same bits again; strided operands; a workspace that is too small is refused."""
+    from gespmm_b200 import capi
+    rng = np.random.default_rng(7000 + K)
+    rowptr, colind, M, N = _mixed_graph(rng)
+    nnz = len(colind)
+    Bf = rng.standard_normal((N, K)).astype(np.float32)
+    vf = rng.standard_normal(nnz).astype(np.float32)
+    rp, ci, vd, Bd = (torch.as_tensor(x, device=dev) for x in (rowptr, colind, vf, Bf))
+    st = torch.cuda.current_stream().cuda_stream
+    short = np.diff(rowptr) <= LONG
+    want = oracle.spmm(rowptr, colind, vf, Bf, fma=True)
+    # bare call, no workspace
+    assert capi.row_sum_is_sequential(K, LONG)
+    C0 = torch.full((M, K), float("nan"), device=dev)
+    capi.csr_spmm_f32(M, N, K, nnz, rp.data_ptr(), ci.data_ptr(), vd.data_ptr(), Bd.data_ptr(), K, C0.data_ptr(), K, st)
+    torch.cuda.synchronize()
+    assert np.array_equal(C0.cpu().numpy()[short], want[short])
+    # with a workspace, sequential flag: bit-identical again; default: within tolerance
+    need = capi.pad_workspace_bytes(M, N, K)
+    assert need >= 4 * (M + N) * ((K + 3) // 4 * 4) and capi.pad_workspace_bytes(M, N, K + (4 - K % 4)) == 0
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    for seq in (True, False):
+        C1 = torch.full((M, K), float("nan"), device=dev)
+        o = capi.opts(sequential=seq, workspace=ws.data_ptr(), workspace_bytes=need)
+        capi.csr_spmm_f32_ex(M, N, K, nnz, rp.data_ptr(), ci.data_ptr(), vd.data_ptr(), Bd.data_ptr(), K, C1.data_ptr(), K, o, st)
+        torch.cuda.synchronize()
+        assert capi.row_sum_is_sequential(K, LONG, o)
+        assert np.array_equal(C1.cpu().numpy()[short], want[short])
+        _check_with(oracle, rowptr, colind, vf, Bf, C1, True)
+    # a graph too sparse for the padding to pay takes the 4-byte-slice walker even with a workspace: same bits
+    rp_s, ci_s = _rand_csr(rng, 20000, N, 30000, empty_frac=0.3)
+    need_s = capi.pad_workspace_bytes(20000, N, K)
+    ws_s = torch.empty(need_s, dtype=torch.uint8, device=dev)
+    Csp = torch.full((20000, K), float("nan"), device=dev)
+    rps, cis = torch.as_tensor(rp_s, device=dev), torch.as_tensor(ci_s, device=dev)
+    capi.csr_spmm_f32_ex(20000, N, K, len(ci_s), rps.data_ptr(), cis.data_ptr(), None, Bd.data_ptr(), K, Csp.data_ptr(), K,
+                         capi.opts(workspace=ws_s.data_ptr(), workspace_bytes=need_s), st)
+    torch.cuda.synchronize()
+    assert np.array_equal(Csp.cpu().numpy(), oracle.spmm(rp_s, ci_s, None, Bf))
+    with pytest.raises(capi.GespmmError):   # a workspace that is too small is refused, not overrun
+        capi.csr_spmm_f32_ex(M, N, K, nnz, rp.data_ptr(), ci.data_ptr(), vd.data_ptr(), Bd.data_ptr(), K, C1.data_ptr(), K,
+                             capi.opts(workspace=ws.data_ptr(), workspace_bytes=need - 256), st)
+    # the operator (hands the library a workspace on its own): bit-identical with and without the sequential flag
+    for Cs in (spmm.csr_spmm_ex(rp, ci, vd, Bd, sequential=True), spmm.csr_spmm(rp, ci, vd, Bd)):
+        torch.cuda.synchronize()
+        assert np.array_equal(Cs.cpu().numpy()[short], want[short])
+        _check(oracle, rowptr, colind, vf, Bf, Cs)
+    # strided B and C through the workspace path
+    ldb, ldc = K + 5, K + 3
+    Bs = torch.zeros(N, ldb, device=dev); Bs[:, :K] = Bd
+    Cst = torch.full((M, ldc), -7.0, device=dev)
+    capi.csr_spmm_f32_ex(M, N, K, nnz, rp.data_ptr(), ci.data_ptr(), vd.data_ptr(), Bs.data_ptr(), ldb, Cst.data_ptr(), ldc,
+                         capi.opts(sequential=True, workspace=ws.data_ptr(), workspace_bytes=need), st)
+    torch.cuda.synchronize()
+    assert np.array_equal(Cst[:, :K].cpu().numpy()[short], want[short]) and bool((Cst[:, K:] == -7.0).all())
 
 
 def test_longest_row_lets_the_call_skip_the_long_row_kernel(spmm, dev, oracle, pkg):
@@ -573,6 +647,12 @@ def test_concurrent_calls_from_host_threads_and_streams(spmm, dev, oracle):
                     out = spmm.csr_spmm_no_edge_value(rp, ci, Bd)
             st.synchronize()
             results[i] = out.cpu().numpy()
+            from gespmm_b200 import capi
+            capi.thread_cleanup()   # this thread's helper stream / events go with it ...
+            out2 = spmm.csr_spmm_no_edge_value(rp, ci, Bd)   # ... and are re-created on demand
+            torch.cuda.synchronize()
+            assert torch.equal(out2, out)
+            capi.thread_cleanup()
         except Exception as e:  # noqa: BLE001
             errors.append(e)
 
