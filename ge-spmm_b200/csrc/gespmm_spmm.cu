@@ -34,14 +34,21 @@
 //   only ever read what they copied themselves, so cp.async.wait_group is the only
 //   synchronisation.  In-flight gather bytes per SM are bounded by shared memory (~100 KB
 //   in flight out of ~200 KB of rings), not by registers.  Unaligned operands / K % 4 != 0
-//   take the register variant (scalar loads, U rows in flight per warp).
+//   take the same walkers on 4-byte slices (cp.async.ca 4 + LDS.32; W = 1), or -- with scratch
+//   memory from the caller -- padded copies of B and C on the 16-byte ones (run_spmm).
+//   WalkerBulk is the same ring fed by one TMA bulk copy (cp.async.bulk + mbarrier) per row.
 //
-// Narrow B (K <= 64, K % 4 == 0)
+// Narrow B (K <= 64 in 16-byte slices, any K <= 16 in 4-byte slices)
 //   A B row then fills only 32/NG lanes' 16-byte slices (NG = 2 / 4 / 8 for K <= 64 / 32 / 16), so the warp is
 //   split into NG lane groups and every copy / read-back instruction serves NG nonzeros at once:
 //   WalkerSub (default) deals consecutive nonzeros of the flat stream to the groups and adds the groups' partial
-//   sums at each row end (re-associated, deterministic); WalkerRows (GESPMM_SEQUENTIAL=1) deals whole rows to the
+//   sums at each row end (re-associated, deterministic); WalkerRows (GESPMM_FLAG_SEQUENTIAL) deals whole rows to the
 //   groups and keeps the sequential order.  1.1-4.8x / 1.2-2.1x the ring walker at these widths.
+//   spmm_rowgroup_kernel: the sequential order for K <= 16 in 4-byte slices (every group sums its own row).
+//
+// Per-call options (gespmm_opts): summation order, the graph's longest row (skips kernel B), a per-gathered-row
+//   scale, a per-stored-row scale and a bias fused into every walker (FUSE: GCNConv's element-wise passes, bit-identical
+//   to running them separately), L2 eviction priorities (HINT), padding workspace.
 //
 // Reductions
 //   sum (the hot path) or max (gespmm_csr_spmm_max_f32: the reference's DGL patch,
