@@ -23,7 +23,7 @@ def is_built():
 
 def build(verbose=False, jobs=None):
     """Compile everything for sm_100a (nvcc cross-compiles without a GPU)."""
-    jobs = jobs or max(1, (os.cpu_count() or 2) // 2)
+    jobs = jobs or max(1, os.cpu_count() or 2)
     cmd = ["make", "-C", HERE, "-j", str(jobs)]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
