@@ -120,6 +120,31 @@ PY
             python scripts/sweep_hot.py --one $cfg > $O/ncu_hot_$cfg.log 2>&1
         note "hotncu $cfg rc=$?"
       done ;;
+    sanitize_odd) # compute-sanitizer: 4-byte-slice ring walker (CLI, K = 41, 100) and the padded route + fused epilogue (operator)
+      python - > $O/sanitize_gen.log 2>&1 <<'PY'
+import sys, numpy as np
+sys.path.insert(0, '.')
+import __graft_entry__ as e
+e.load_package()
+from gespmm_b200 import graphs
+rng = np.random.default_rng(0)
+M = 3000
+deg = rng.integers(0, 9, M); deg[rng.random(M) < 0.3] = 0
+deg[[5, 700, 701, 2999]] = [40000, 5000, 4097, 9000]
+deg[100:140] = rng.integers(30, 300, 40)
+rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+colind = rng.integers(0, M, rowptr[-1]).astype(np.int32)
+graphs.write_mtx('gpurun_out/sanitize.mtx', rowptr, colind)
+PY
+      for tool in memcheck racecheck; do
+        echo "== $tool, CLI (bare C ABI: 4-byte-slice ring walker), K=41,47,127" >> $O/sanitize_odd.txt
+        timeout 300 compute-sanitizer --tool $tool --error-exitcode 9 ge-spmm_b200/bin/spmm_test $O/sanitize.mtx 0 \
+            --K 41,47,127 --iters 2 --validate --out $O/sanitize.csv 2>&1 | grep -E "SUMMARY|validate|WA|Error|error" | head -12 >> $O/sanitize_odd.txt
+        echo "== $tool, operator (padded route, sequential + fused epilogue), K=41" >> $O/sanitize_odd.txt
+        timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_spmm_gpu.py -q -m gpu -x \
+            -k "widths_that_are_not and 41 or fused_scales and 41" 2>&1 | grep -E "SUMMARY|passed|failed|Error|error" | head -12 >> $O/sanitize_odd.txt
+      done
+      note "sanitize_odd done" ;;
     rows)     # sub-warp (2) vs row-parallel (4) narrow walkers on every shape
       timeout 600 python scripts/sweep_narrow.py --variants 2,4 --tasks 0 > $O/sweep_v24.txt 2> $O/sweep_v24.err; note "rows rc=$?" ;;
     auto64)   # the SpMM suite with the sub-warp walker chosen automatically for K <= 64

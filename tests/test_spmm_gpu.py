@@ -712,6 +712,106 @@ def test_full_size_citpatents_shape_properties(spmm, dev, oracle, pkg):
         assert np.array_equal(C[r].cpu().numpy(), want[0])
 
 
+def _sample_rows_vs_oracle(oracle, rowptr, colind, val, B, C, rows):
+    """Rows `rows` of C against the oracle, one small CSR per row (full-size graphs: the whole product is too slow on the CPU)."""
+    rp_h, ci_h = rowptr.cpu().numpy(), colind.cpu().numpy()
+    v_h = None if val is None else val.cpu().numpy()
+    B_h = B.cpu().numpy()
+    for r in rows:
+        s, e = int(rp_h[r]), int(rp_h[r + 1])
+        want = oracle.spmm(np.array([0, e - s], np.int32), ci_h[s:e], None if v_h is None else v_h[s:e], B_h)
+        assert np.array_equal(C[r].cpu().numpy(), want[0]), r
+
+
+def test_full_size_reddit_shape_through_spmmfunction(dev, oracle, pkg, request):
+    """BASELINE.json configs[2] at full size: the Reddit shape (232,965 nodes, 114,615,892 edges, symmetric), K = 256,
+    forward AND backward through SPMMFunction.apply (op.py:8-36; symmetric graph, so the CSC arrays are the CSR arrays).
+    (i) feat == 1: forward gives the degree exactly, and so does the gradient of sum(out); (ii) integer-valued features:
+    the column sums of out equal the degree-weighted column sums of feat computed independently, exactly; (iii) real-valued
+    features: sampled rows (the longest included) equal the oracle bit for bit up to GESPMM_LONG_ROW nonzeros and within 1e-4
+    above; (iv) the reference's own extension, built from its sources, gives the same bits on every row up to GESPMM_LONG_ROW."""
+    from gespmm_b200 import graphs
+    from gespmm_b200.op import SPMMFunction
+    N, nnz = graphs.SHAPES["reddit"]
+    K = 256
+    rowptr, colind = graphs.reddit_like(seed=2, device=dev)
+    assert rowptr.numel() == N + 1 and colind.numel() == nnz
+    deg = (rowptr[1:] - rowptr[:-1])
+    x = torch.ones(N, K, device=dev, requires_grad=True)
+    y = SPMMFunction.apply(rowptr, colind, rowptr, colind, x)
+    assert torch.equal(y.detach(), deg.float()[:, None].expand(-1, K))
+    y.sum().backward()
+    assert torch.equal(x.grad, deg.float()[:, None].expand(-1, K))       # A^T 1 = in-degree = degree (symmetric)
+    del x, y
+    g = torch.Generator(device=dev).manual_seed(5)
+    xi = torch.randint(-4, 5, (N, K), generator=g, device=dev).float()
+    yi = SPMMFunction.apply(rowptr, colind, rowptr, colind, xi)
+    assert torch.equal(yi.double().sum(0), deg.double() @ xi.double())
+    del xi, yi
+    xf = torch.randn(N, K, generator=g, device=dev)
+    yf = SPMMFunction.apply(rowptr, colind, rowptr, colind, xf)
+    order = torch.argsort(deg, descending=True).cpu().tolist()
+    short_rows = [r for r in order if int(deg[r]) <= LONG][:3] + torch.randint(0, N, (40,), generator=torch.Generator().manual_seed(1)).tolist()
+    _sample_rows_vs_oracle(oracle, rowptr, colind, None, xf, yf, [r for r in short_rows if int(deg[r]) <= LONG])
+    for r in order[:2]:                                                    # the two longest rows: segmented, within tolerance
+        s, e = int(rowptr[r]), int(rowptr[r + 1])
+        G, mag = oracle.spmm_f64(np.array([0, e - s], np.int32), colind[s:e].cpu().numpy(), None, xf.cpu().numpy())
+        assert (np.abs(yf[r].cpu().numpy().astype(np.float64) - G[0]) <= RTOL * np.maximum(np.abs(G[0]), mag[0]) + 1e-30).all()
+    if oracle.have_ref(oracle.REF_EXT):
+        ref = request.getfixturevalue("ref_ext")
+        yr = ref.csr_spmm_no_edge_value(rowptr, colind, xf)
+        torch.cuda.synchronize()
+        short = deg <= LONG
+        assert torch.equal(yf[short], yr[short]), "must be bit-identical to pytorch-custom/spmm_kernel.cu at configs[2]'s full size"
+
+
+@pytest.mark.parametrize("K", [32, 47, 64, 128])
+def test_full_size_products_shape_properties(spmm, dev, oracle, pkg, K):
+    """BASELINE.json configs[3] at full size: the ogbn-products shape (2,449,029 nodes, ~123.7 M edges), K from the sweep
+    plus the graph's real class count (47).  feat == 1 gives the degree exactly (integer sums are exact in any order);
+    real-valued features: sampled rows against the oracle, bit for bit where the operator sums in CSR order (K = 47, 128),
+    within 1e-4 where it re-associates (K = 32, 64)."""
+    from gespmm_b200 import graphs
+    rowptr, colind = graphs.products_like(seed=3, device=dev)
+    N = rowptr.numel() - 1
+    deg = (rowptr[1:] - rowptr[:-1])
+    C = spmm.csr_spmm_no_edge_value(rowptr, colind, torch.ones(N, K, device=dev))
+    assert torch.equal(C, deg.float()[:, None].expand(-1, K))
+    del C
+    g = torch.Generator(device=dev).manual_seed(9)
+    B = torch.randn(N, K, generator=g, device=dev)
+    val = torch.randn(colind.numel(), generator=g, device=dev)
+    C = spmm.csr_spmm(rowptr, colind, val, B)
+    rows = [r for r in torch.randint(0, N, (60,), generator=torch.Generator().manual_seed(2)).tolist() if int(deg[r]) <= LONG]
+    if spmm.row_sum_is_sequential(K, 2):
+        _sample_rows_vs_oracle(oracle, rowptr, colind, val, B, C, rows)
+    else:
+        B_h = B.cpu().numpy()
+        for r in rows:
+            s, e = int(rowptr[r]), int(rowptr[r + 1])
+            G, mag = oracle.spmm_f64(np.array([0, e - s], np.int32), colind[s:e].cpu().numpy(), val[s:e].cpu().numpy(), B_h)
+            assert (np.abs(C[r].cpu().numpy().astype(np.float64) - G[0]) <= RTOL * np.maximum(np.abs(G[0]), mag[0]) + 1e-30).all()
+
+
+def test_full_size_rmat_shape_properties(spmm, dev, oracle, pkg):
+    """BASELINE.json configs[4] on one GPU at full size: R-MAT 10M x 10M, 200M nonzeros (duplicates kept), K = 128.
+    feat == 1 gives the degree exactly on every row -- the hub row of 275,760 nonzeros (cluster path) included --; sampled
+    rows of a real-valued product equal the oracle bit for bit."""
+    from gespmm_b200 import graphs
+    rowptr, colind = graphs.rmat(seed=4, device=dev)
+    N, K = rowptr.numel() - 1, 128
+    assert N == 10_000_000 and colind.numel() == 200_000_000
+    deg = (rowptr[1:] - rowptr[:-1])
+    assert int(deg.max()) > 32768                                           # exercises the whole-cluster long-row path
+    C = spmm.csr_spmm_no_edge_value(rowptr, colind, torch.ones(N, K, device=dev))
+    assert torch.equal(C, deg.float()[:, None].expand(-1, K))
+    del C
+    B = torch.randn(N, K, generator=torch.Generator(device=dev).manual_seed(4), device=dev)
+    C = spmm.csr_spmm_no_edge_value(rowptr, colind, B)
+    rows = [r for r in torch.randint(0, N, (60,), generator=torch.Generator().manual_seed(6)).tolist() if int(deg[r]) <= LONG]
+    _sample_rows_vs_oracle(oracle, rowptr, colind, None, B, C, rows)
+
+
 # ---- csr2csc, autograd, GCNConv ------------------------------------------------------------------------
 
 @pytest.mark.parametrize("M,N,nnz", [(1, 1, 1), (50, 70, 0), (300, 200, 5000), (5000, 70000, 200000), (2000, 3, 30000)])
