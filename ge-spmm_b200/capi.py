@@ -69,7 +69,7 @@ def lib():
         L.gespmm_reload_env.restype = None
         L.gespmm_reload_env.argtypes = []
         L.gespmm_pad_workspace_bytes.restype = sz
-        L.gespmm_pad_workspace_bytes.argtypes = [i64, i64, i64]
+        L.gespmm_pad_workspace_bytes.argtypes = [i64, i64, i64, i64]
         L.gespmm_thread_cleanup.restype = None
         L.gespmm_thread_cleanup.argtypes = []
         L.gespmm_row_sum_is_sequential_ex.restype = ctypes.c_int
@@ -164,9 +164,9 @@ def max_row_nnz(M, rowptr, stream=None):
     return int(out.value)
 
 
-def pad_workspace_bytes(M, N, K):
-    """Bytes of Opts.workspace that let an odd width K > 16 run on the 16-byte-slice walkers (0: does not apply)."""
-    return int(lib().gespmm_pad_workspace_bytes(int(M), int(N), int(K)))
+def pad_workspace_bytes(M, N, K, nnz):
+    """Bytes of Opts.workspace that let an odd width K > 16 run on the 16-byte-slice walkers (0: the library would not pad)."""
+    return int(lib().gespmm_pad_workspace_bytes(int(M), int(N), int(K), int(nnz)))
 
 
 def thread_cleanup():

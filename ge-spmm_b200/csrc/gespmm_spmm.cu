@@ -117,7 +117,7 @@ bool use_subwarp(int64_t K, int walker)
     return walker == GESPMM_WALKER_AUTO && K <= tuning().subwarp_max_k;
 }
 
-// `mode`: 0 sum, 1 max, 2 fused sum (scales / bias)
+// `mode`: 0 sum, 1 max, 2 fused sum with a gathered-row scale, 3 fused sum without one (row scale / bias only)
 cudaError_t dispatch_all(bool valued, int mode, bool vec4, bool peer, int walker, bool hint, int V, bool masked, int K, const Args &a)
 {
     if (!vec4 && K <= kRowGroupMaxK && walker != GESPMM_WALKER_REGISTER) {
@@ -296,7 +296,7 @@ int run_spmm(int64_t M, int64_t N, int64_t K, int64_t nnz, const int32_t *rowptr
     a.op.l2_near = ch.l2_policy & 3; a.op.l2_far = (ch.l2_policy >> 2) & 3; a.op.l2_store = (ch.l2_policy >> 4) & 3;
     a.op.l2_window = ch.l2_window;
     a.op.l2_hot = ch.hot;
-    const int mode = max_reduce ? 1 : (ch.fuse() ? 2 : 0);
+    const int mode = max_reduce ? 1 : (ch.fuse() ? (ch.col_scale ? 2 : 3) : 0);  // 3: row scale / bias only, nothing per nonzero
     const bool hint = ch.l2_policy > 0 && mode == 0;
     const cudaError_t err = dispatch_all(val != nullptr, mode, vec4, parts > 0, ch.walker, hint, V, masked, (int)K, a);
     return err == cudaSuccess ? GESPMM_OK : GESPMM_ERR_CUDA;
@@ -316,9 +316,9 @@ int sequential_for(int64_t K, int64_t row_nnz, const Choice &ch)
 
 }  // namespace
 
-extern "C" size_t gespmm_pad_workspace_bytes(int64_t M, int64_t N, int64_t K)
+extern "C" size_t gespmm_pad_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t nnz)
 {
-    if (M < 0 || N < 0 || K <= kRowGroupMaxK || K % 4 == 0) return 0;
+    if (M < 0 || N < 0 || K <= kRowGroupMaxK || K % 4 == 0 || nnz < 4 * (M + N)) return 0;
     return pad_workspace_bytes(M, N, K);
 }
 

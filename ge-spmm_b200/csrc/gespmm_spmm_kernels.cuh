@@ -170,8 +170,11 @@ struct Reduce {
     using T = typename P::T;
     static_assert(!(FUSE && MAXR), "the fused scaling belongs to the sum");
     static __device__ __forceinline__ T start(float init) { return MAXR ? P::splat(init) : P::zero(); }
+    // SC: the gathered row is scaled (a fused walker whose call carries a col_scale); without it a fused walker's step
+    // is the plain one -- the row scale and the bias cost nothing per nonzero
+    template <bool SC = true>
     static __device__ __forceinline__ void step(T &acc, float a, const T &b, float s = 1.f) {
-        if (FUSE) {
+        if (FUSE && SC) {
             const T t = P::mul_rn(b, s);
             if (VALUED) P::fma(acc, a, t); else P::add_rn(acc, t);
         } else if (MAXR) { if (VALUED) P::mx(acc, P::scaled(a, b)); else P::mx(acc, b); }
@@ -458,9 +461,11 @@ __device__ __forceinline__ float4 lds128(unsigned saddr)
 //       between the column and the rows being summed (bit 31 of the token = "far"); C stores carry one too.
 // W = floats per lane and pack: 4 (16-byte slices: K % 4 == 0, aligned operands) or 1 (4-byte slices: any K, any 4-byte
 //     alignment; cp.async.ca, the only 4-byte form) -- a pack is then 128 columns / 512 bytes or 32 columns / 128 bytes.
+// SCALE (fused walkers): the call carries a col_scale; without it (row scale / bias only) nothing is added per nonzero.
 template <int V, bool VALUED, int G, int NS, int CP, bool MASKED, bool PEER = false, bool MAXR = false, bool FUSE = false,
-          bool HINT = false, int W = 4>
+          bool HINT = false, int W = 4, bool SCALE = FUSE>
 struct WalkerRing {
+    static_assert(FUSE || !SCALE, "the gathered-row scale belongs to the fused walkers");
     static_assert(W == 4 || (W == 1 && !PEER && !HINT), "4-byte slices: local B, no L2 hints");
     using R = Reduce<Pack<W == 4>, VALUED, MAXR, FUSE>;
     using E = Epilogue<Pack<W == 4>, FUSE>;
@@ -549,7 +554,7 @@ struct WalkerRing {
     }
     // FUSE: the scale of the column a token names (1 when there is no col_scale)
     __device__ __forceinline__ float load_scale(Tok t, bool on) const {
-        if constexpr (FUSE && !PEER) return (on && col_scale) ? __ldg(col_scale + t) : 1.f;
+        if constexpr (SCALE && !PEER) return (on && col_scale) ? __ldg(col_scale + t) : 1.f;
         else return 1.f;
     }
 
@@ -617,7 +622,7 @@ struct WalkerRing {
         for (int v = 0; v < V; v++) acc[v] = start();
     }
 
-    template <bool FULL>
+    template <bool FULL, bool SC>
     __device__ __forceinline__ void consume_impl(float vals, float scales, int pos0, int n, unsigned endmask, T (&acc)[V],
                                                  unsigned &rows_left, int rb, unsigned slot) const {
 #pragma unroll
@@ -628,7 +633,7 @@ struct WalkerRing {
 #pragma unroll
             for (int i = 0; i < UB; i++) {
                 if (VALUED) a[i] = __shfl_sync(kFull, vals, pos0 + i0 + i);
-                if (FUSE) sc[i] = __shfl_sync(kFull, scales, pos0 + i0 + i);
+                if (SC) sc[i] = __shfl_sync(kFull, scales, pos0 + i0 + i);
                 if (FULL || pos0 + i0 + i < n) {
 #pragma unroll
                     for (int v = 0; v < V; v++)
@@ -643,14 +648,14 @@ struct WalkerRing {
 #pragma unroll
                 for (int i = 0; i < UB; i++) {
 #pragma unroll
-                    for (int v = 0; v < V; v++) R::step(acc[v], VALUED ? a[i] : 1.f, b[i][v], FUSE ? sc[i] : 1.f);
+                    for (int v = 0; v < V; v++) R::template step<SC>(acc[v], VALUED ? a[i] : 1.f, b[i][v], SC ? sc[i] : 1.f);
                 }
             } else {
 #pragma unroll
                 for (int i = 0; i < UB; i++) {
                     if (FULL || pos0 + i0 + i < n) {
 #pragma unroll
-                        for (int v = 0; v < V; v++) R::step(acc[v], VALUED ? a[i] : 1.f, b[i][v], FUSE ? sc[i] : 1.f);
+                        for (int v = 0; v < V; v++) R::template step<SC>(acc[v], VALUED ? a[i] : 1.f, b[i][v], SC ? sc[i] : 1.f);
                         if (ends & (1u << i)) flush(acc, rows_left, rb);
                     }
                 }
@@ -659,8 +664,8 @@ struct WalkerRing {
     }
     __device__ __forceinline__ void consume(float vals, float scales, int pos0, int n, unsigned endmask, T (&acc)[V],
                                             unsigned &rows_left, int rb, unsigned slot) const {
-        if (pos0 + G <= n) consume_impl<true>(vals, scales, pos0, n, endmask, acc, rows_left, rb, slot);
-        else consume_impl<false>(vals, scales, pos0, n, endmask, acc, rows_left, rb, slot);
+        if (pos0 + G <= n) consume_impl<true, SCALE>(vals, scales, pos0, n, endmask, acc, rows_left, rb, slot);
+        else consume_impl<false, SCALE>(vals, scales, pos0, n, endmask, acc, rows_left, rb, slot);
     }
 
     __device__ __forceinline__ void stream(int s, int e, T (&acc)[V], int my_end, unsigned rows, int rb) {
@@ -673,7 +678,7 @@ struct WalkerRing {
             if (VALUED) cval = __ldcs(val + s + lane);
         }
         if (s + 32 + lane < e) ncol = load_tok(s + 32 + lane);
-        if constexpr (FUSE) csc = load_scale(ccol, s + lane < e);
+        if constexpr (SCALE) csc = load_scale(ccol, s + lane < e);
         const bool my_row = (rows >> lane) & 1u;
         unsigned rows_left = rows;
 #pragma unroll
@@ -682,7 +687,7 @@ struct WalkerRing {
         for (int p0 = s; p0 < e; p0 += 32) {
             if (p0 + 64 + lane < e) fcol = load_tok(p0 + 64 + lane);
             if (VALUED && p0 + 32 + lane < e) nval = __ldcs(val + p0 + 32 + lane);
-            if constexpr (FUSE) nsc = load_scale(ncol, p0 + 32 + lane < e);  // ncol arrived one iteration ago
+            if constexpr (SCALE) nsc = load_scale(ncol, p0 + 32 + lane < e);  // ncol arrived one iteration ago
             const unsigned rel = (unsigned)(my_end - 1 - p0);
             const unsigned endmask = __reduce_or_sync(kFull, (my_row && rel < 32u) ? (1u << rel) : 0u);
             const int n = min(32, e - p0);
@@ -697,7 +702,7 @@ struct WalkerRing {
                 consume(cval, csc, j * G, n, endmask, acc, rows_left, rb, (j & (NS - 1)) * kStageBytes);
             }
             ccol = ncol; ncol = fcol; cval = nval;
-            if constexpr (FUSE) csc = nsc;
+            if constexpr (SCALE) csc = nsc;
         }
         cp_async_wait<0>();
     }
@@ -905,7 +910,7 @@ struct WalkerBulk {
 // still bit-identical).  gespmm_row_sum_is_sequential() tells callers which rows that applies to.
 // W = floats per lane: 4 (16-byte slices: K % 4 == 0, aligned operands) or 1 (4-byte slices: ANY K <= 32 / NG and any
 // 4-byte alignment -- the class-count widths of a GCN's last layer, K = 3, 7, ...; cp.async.ca, the only 4-byte form).
-template <int NG, bool VALUED, bool MAXR = false, bool FUSE = false, int W = 4>
+template <int NG, bool VALUED, bool MAXR = false, bool FUSE = false, int W = 4, bool SCALE = FUSE>
 struct WalkerSub {
     using P = Pack<W == 4>;
     using T = typename P::T;
@@ -963,7 +968,7 @@ struct WalkerSub {
         if constexpr (FUSE) my_rs = (row_scale && lane < nrows) ? __ldg(row_scale + rb + lane) : 1.f;
     }
     __device__ __forceinline__ float load_scale(int c, bool on) const {
-        if constexpr (FUSE) return (on && col_scale) ? __ldg(col_scale + c) : 1.f;
+        if constexpr (SCALE) return (on && col_scale) ? __ldg(col_scale + c) : 1.f;
         else return 1.f;
     }
 
@@ -1027,7 +1032,7 @@ struct WalkerSub {
         else issue_impl<false>(cols, pos0, n, slot);
     }
 
-    template <bool FULL>
+    template <bool FULL, bool SC>
     __device__ __forceinline__ void consume_impl(float vals, float scales, int pos0, int n, unsigned endmask, T &acc,
                                                  unsigned &rows_left, int rb, unsigned slot) const {
 #pragma unroll
@@ -1040,13 +1045,13 @@ struct WalkerSub {
                 // read back unconditionally: a slice that was not copied this time (nonzero beyond n, columns
                 // beyond K) holds stale ring bytes that are never added to anything that is stored
                 a[i] = VALUED ? __shfl_sync(kFull, vals, pos0 + (i0 + i) * NG + g) : 1.f;
-                sc[i] = FUSE ? __shfl_sync(kFull, scales, pos0 + (i0 + i) * NG + g) : 1.f;
+                sc[i] = SC ? __shfl_sync(kFull, scales, pos0 + (i0 + i) * NG + g) : 1.f;
                 if constexpr (W == 4) b[i] = lds128(ring + slot + (i0 + i) * kRowBytes);
                 else b[i] = lds32(ring + slot + (i0 + i) * kRowBytes);
             }
             if (FULL && ((endmask >> (pos0 + i0 * NG)) & low_bits(UB * NG)) == 0u) {  // no row ends in these UB quads
 #pragma unroll
-                for (int i = 0; i < UB; i++) R::step(acc, a[i], b[i], sc[i]);
+                for (int i = 0; i < UB; i++) R::template step<SC>(acc, a[i], b[i], sc[i]);
                 continue;
             }
 #pragma unroll
@@ -1054,25 +1059,25 @@ struct WalkerSub {
                 const bool live = FULL || (pos0 + (i0 + i) * NG + g < n);
                 unsigned e4 = (endmask >> (pos0 + (i0 + i) * NG)) & ((1u << NG) - 1u);  // bit x: a row ends at group x's nonzero
                 if (e4 == 0u) {  // warp-uniform: no row ends inside this quad (the common case for rows >> NG)
-                    if (live) R::step(acc, a[i], b[i], sc[i]);
+                    if (live) R::template step<SC>(acc, a[i], b[i], sc[i]);
                 } else {
                     int lo = 0;  // groups below `lo` already added their nonzero of this quad (to an earlier row)
                     do {
                         const int hi = __ffs(e4) - 1;
-                        if (live && g >= lo && g <= hi) R::step(acc, a[i], b[i], sc[i]);
+                        if (live && g >= lo && g <= hi) R::template step<SC>(acc, a[i], b[i], sc[i]);
                         flush(acc, rows_left, rb);
                         lo = hi + 1;
                         e4 &= e4 - 1;
                     } while (e4);
-                    if (live && g >= lo) R::step(acc, a[i], b[i], sc[i]);
+                    if (live && g >= lo) R::template step<SC>(acc, a[i], b[i], sc[i]);
                 }
             }
         }
     }
     __device__ __forceinline__ void consume(float vals, float scales, int pos0, int n, unsigned endmask, T &acc,
                                             unsigned &rows_left, int rb, unsigned slot) const {
-        if (pos0 + SN <= n) consume_impl<true>(vals, scales, pos0, n, endmask, acc, rows_left, rb, slot);
-        else consume_impl<false>(vals, scales, pos0, n, endmask, acc, rows_left, rb, slot);
+        if (pos0 + SN <= n) consume_impl<true, SCALE>(vals, scales, pos0, n, endmask, acc, rows_left, rb, slot);
+        else consume_impl<false, SCALE>(vals, scales, pos0, n, endmask, acc, rows_left, rb, slot);
     }
 
     // same contract as WalkerRing::stream; with rows == 0 the groups' partials are left in acc (see finish)
@@ -1085,7 +1090,7 @@ struct WalkerSub {
             if (VALUED) cval = __ldcs(val + s + lane);
         }
         if (s + 32 + lane < e) ncol = __ldcs(colind + s + 32 + lane);
-        if constexpr (FUSE) csc = load_scale(ccol, s + lane < e);
+        if constexpr (SCALE) csc = load_scale(ccol, s + lane < e);
         const bool my_row = (rows >> lane) & 1u;
         unsigned rows_left = rows;
         unsigned slot = 0;  // stage being consumed; the other one is being filled
@@ -1094,7 +1099,7 @@ struct WalkerSub {
         for (int p0 = s; p0 < e; p0 += 32) {
             if (p0 + 64 + lane < e) fcol = __ldcs(colind + p0 + 64 + lane);
             if (VALUED && p0 + 32 + lane < e) nval = __ldcs(val + p0 + 32 + lane);
-            if constexpr (FUSE) nsc = load_scale(ncol, p0 + 32 + lane < e);
+            if constexpr (SCALE) nsc = load_scale(ncol, p0 + 32 + lane < e);
             const unsigned rel = (unsigned)(my_end - 1 - p0);
             const unsigned endmask = __reduce_or_sync(kFull, (my_row && rel < 32u) ? (1u << rel) : 0u);
             const int n = min(32, e - p0);
@@ -1109,7 +1114,7 @@ struct WalkerSub {
                 slot ^= kStageBytes;
             }
             ccol = ncol; ncol = fcol; cval = nval;
-            if constexpr (FUSE) csc = nsc;
+            if constexpr (SCALE) csc = nsc;
         }
         cp_async_wait<0>();
     }
@@ -1129,7 +1134,7 @@ struct WalkerSub {
 // run takes as many chunks as its longest group needs (measured on the generators' degree
 // distributions: 95-97 % of ideal at NG = 2, 82-92 % at NG = 4, 53-73 % at NG = 8).
 // Rows only; kernel B (long rows, re-associated anyway) pairs it with WalkerSub.
-template <int NG, bool VALUED, bool MAXR = false, bool FUSE = false>
+template <int NG, bool VALUED, bool MAXR = false, bool FUSE = false, bool SCALE = FUSE>
 struct WalkerRows {
     using P = Pack<true>;
     using T = float4;
@@ -1183,7 +1188,7 @@ struct WalkerRows {
         if constexpr (FUSE) my_rs = (row_scale && lane < nrows) ? __ldg(row_scale + rb + lane) : 1.f;
     }
     __device__ __forceinline__ float load_scale(int c, bool on) const {
-        if constexpr (FUSE) return (on && col_scale) ? __ldg(col_scale + c) : 1.f;
+        if constexpr (SCALE) return (on && col_scale) ? __ldg(col_scale + c) : 1.f;
         else return 1.f;
     }
 
@@ -1214,6 +1219,11 @@ struct WalkerRows {
     // steps [k0, k0 + QS) of the chunk: n = my group's nonzeros left, nmin = the least over the groups
     __device__ __forceinline__ void consume(float vals, float scales, int k0, int n, int nmin, unsigned endmask, T &acc,
                                             unsigned &left, int rb, unsigned slot) const {
+        consume_impl<SCALE>(vals, scales, k0, n, nmin, endmask, acc, left, rb, slot);
+    }
+    template <bool SC>
+    __device__ __forceinline__ void consume_impl(float vals, float scales, int k0, int n, int nmin, unsigned endmask, T &acc,
+                                                 unsigned &left, int rb, unsigned slot) const {
 #pragma unroll
         for (int i0 = 0; i0 < QS; i0 += UB) {
             T b[UB];
@@ -1222,18 +1232,18 @@ struct WalkerRows {
 #pragma unroll
             for (int i = 0; i < UB; i++) {
                 a[i] = VALUED ? __shfl_sync(kFull, vals, k0 + i0 + i, LPR) : 1.f;
-                sc[i] = FUSE ? __shfl_sync(kFull, scales, k0 + i0 + i, LPR) : 1.f;
+                sc[i] = SC ? __shfl_sync(kFull, scales, k0 + i0 + i, LPR) : 1.f;
                 b[i] = lds128(ring + slot + (i0 + i) * 512);  // stale bytes where nothing was copied: never added
             }
             const unsigned ends = endmask & ((kGroupOnes * ((1u << UB) - 1u)) << (k0 + i0));  // any group, these UB steps
             if (ends == 0u && nmin >= k0 + i0 + UB) {  // warp-uniform: every group is live and no row ends
 #pragma unroll
-                for (int i = 0; i < UB; i++) R::step(acc, a[i], b[i], sc[i]);
+                for (int i = 0; i < UB; i++) R::template step<SC>(acc, a[i], b[i], sc[i]);
             } else {
 #pragma unroll
                 for (int i = 0; i < UB; i++) {
                     const int k = k0 + i0 + i;
-                    if (k < n) R::step(acc, a[i], b[i], sc[i]);
+                    if (k < n) R::template step<SC>(acc, a[i], b[i], sc[i]);
                     const int rel = (__ffs(left) - 1) & 31;  // my group's current row (any lane when the group is done)
                     float rs = 1.f;
                     if constexpr (FUSE) rs = __shfl_sync(kFull, my_rs, rel);  // every lane takes part: the groups diverge below
@@ -1280,14 +1290,14 @@ struct WalkerRows {
             if (VALUED) cval = __ldcs(val + p + sl);
         }
         if (p + LPR + sl < ge) ncol = __ldcs(colind + p + LPR + sl);
-        if constexpr (FUSE) csc = load_scale(ccol, p + sl < ge);
+        if constexpr (SCALE) csc = load_scale(ccol, p + sl < ge);
         unsigned slot = 0;
         issue(ccol, 0, ge - p, 0);
 #pragma unroll 1
         for (int c0 = 0; c0 < maxlen; c0 += LPR, p += LPR) {
             if (p + 2 * LPR + sl < ge) fcol = __ldcs(colind + p + 2 * LPR + sl);
             if (VALUED && p + LPR + sl < ge) nval = __ldcs(val + p + LPR + sl);
-            if constexpr (FUSE) nsc = load_scale(ncol, p + LPR + sl < ge);
+            if constexpr (SCALE) nsc = load_scale(ncol, p + LPR + sl < ge);
             // row ends of every group inside this chunk: one LPR-bit field per group
             const unsigned rel = (unsigned)(my_end - 1 - (row_gs + c0));
             const unsigned endmask = __reduce_or_sync(kFull, (my_row && rel < (unsigned)LPR) ? (1u << (grp * LPR + rel)) : 0u);
@@ -1303,7 +1313,7 @@ struct WalkerRows {
                 slot ^= kStageBytes;
             }
             ccol = ncol; ncol = fcol; cval = nval;
-            if constexpr (FUSE) csc = nsc;
+            if constexpr (SCALE) csc = nsc;
         }
         cp_async_wait<0>();
         accv[0] = acc;
@@ -1811,12 +1821,12 @@ template <> struct Shape<2> { static constexpr int G = 4, MINB = 20; };
 template <> struct Shape<3> { static constexpr int G = 2, MINB = 24; };
 template <> struct Shape<4> { static constexpr int G = 2, MINB = 16; };
 
-template <int V, bool VALUED, bool PEER, bool MAXR, bool FUSE = false, bool HINT = false>
+template <int V, bool VALUED, bool PEER, bool MAXR, bool FUSE = false, bool HINT = false, bool SCALE = FUSE>
 cudaError_t launch_ring(const Args &a, bool masked)
 {
     constexpr int G = Shape<V>::G, MINB = Shape<V>::MINB;
-    return masked ? launch<WalkerRing<V, VALUED, G, 2, 0, true, PEER, MAXR, FUSE, HINT>, V, true, MINB>(a)
-                  : launch<WalkerRing<V, VALUED, G, 2, 0, false, PEER, MAXR, FUSE, HINT>, V, true, MINB>(a);
+    return masked ? launch<WalkerRing<V, VALUED, G, 2, 0, true, PEER, MAXR, FUSE, HINT, 4, SCALE>, V, true, MINB>(a)
+                  : launch<WalkerRing<V, VALUED, G, 2, 0, false, PEER, MAXR, FUSE, HINT, 4, SCALE>, V, true, MINB>(a);
 }
 template <bool VALUED, bool PEER, bool MAXR>
 cudaError_t dispatch_ring(int V, const Args &a, bool masked)
@@ -1830,49 +1840,49 @@ cudaError_t dispatch_ring(int V, const Args &a, bool masked)
 }
 
 // Narrow B (K <= 64, aligned operands): NG = 2 / 4 / 8 nonzeros per warp-wide copy for K <= 64 / 32 / 16.
-template <bool VALUED, bool MAXR, bool FUSE>
+template <bool VALUED, bool MAXR, bool FUSE, bool SCALE = FUSE>
 cudaError_t dispatch_sub(int K, const Args &a)
 {
-    if (K > 32) return launch<WalkerSub<2, VALUED, MAXR, FUSE>, 1, true, 24>(a);
-    if (K > 16) return launch<WalkerSub<4, VALUED, MAXR, FUSE>, 1, true, 24>(a);
-    return launch<WalkerSub<8, VALUED, MAXR, FUSE>, 1, true, 24>(a);
+    if (K > 32) return launch<WalkerSub<2, VALUED, MAXR, FUSE, 4, SCALE>, 1, true, 24>(a);
+    if (K > 16) return launch<WalkerSub<4, VALUED, MAXR, FUSE, 4, SCALE>, 1, true, 24>(a);
+    return launch<WalkerSub<8, VALUED, MAXR, FUSE, 4, SCALE>, 1, true, 24>(a);
 }
 
 // Narrow B that is not made of 16-byte slices (any K <= 16, any 4-byte alignment): the same walker on 4-byte slices,
 // NG = 2 / 4 / 8 nonzeros per warp-wide copy for K <= 16 / 8 / 4.
-template <bool VALUED, bool MAXR, bool FUSE>
+template <bool VALUED, bool MAXR, bool FUSE, bool SCALE = FUSE>
 cudaError_t dispatch_sub1(int K, const Args &a)
 {
-    if (K > 8) return launch<WalkerSub<2, VALUED, MAXR, FUSE, 1>, 1, false, 24>(a);
-    if (K > 4) return launch<WalkerSub<4, VALUED, MAXR, FUSE, 1>, 1, false, 24>(a);
-    return launch<WalkerSub<8, VALUED, MAXR, FUSE, 1>, 1, false, 24>(a);
+    if (K > 8) return launch<WalkerSub<2, VALUED, MAXR, FUSE, 1, SCALE>, 1, false, 24>(a);
+    if (K > 4) return launch<WalkerSub<4, VALUED, MAXR, FUSE, 1, SCALE>, 1, false, 24>(a);
+    return launch<WalkerSub<8, VALUED, MAXR, FUSE, 1, SCALE>, 1, false, 24>(a);
 }
 
 // The row-parallel narrow walker (sequential order); long rows go to kernel B with the sub-warp walker.
-template <bool VALUED, bool MAXR, bool FUSE>
+template <bool VALUED, bool MAXR, bool FUSE, bool SCALE = FUSE>
 cudaError_t dispatch_rows(int K, const Args &a)
 {
-    if (K > 32) return launch<WalkerRows<2, VALUED, MAXR, FUSE>, 1, true, 24, WalkerSub<2, VALUED, MAXR, FUSE>>(a);
-    if (K > 16) return launch<WalkerRows<4, VALUED, MAXR, FUSE>, 1, true, 24, WalkerSub<4, VALUED, MAXR, FUSE>>(a);
-    return launch<WalkerRows<8, VALUED, MAXR, FUSE>, 1, true, 24, WalkerSub<8, VALUED, MAXR, FUSE>>(a);
+    if (K > 32) return launch<WalkerRows<2, VALUED, MAXR, FUSE, SCALE>, 1, true, 24, WalkerSub<2, VALUED, MAXR, FUSE, 4, SCALE>>(a);
+    if (K > 16) return launch<WalkerRows<4, VALUED, MAXR, FUSE, SCALE>, 1, true, 24, WalkerSub<4, VALUED, MAXR, FUSE, 4, SCALE>>(a);
+    return launch<WalkerRows<8, VALUED, MAXR, FUSE, SCALE>, 1, true, 24, WalkerSub<8, VALUED, MAXR, FUSE, 4, SCALE>>(a);
 }
 
 // Any K, any 4-byte alignment, above the lane-group walkers' K <= 16: the ring walker on 4-byte slices -- 32 columns per
 // pack, up to 4 packs per lane (128-column panels), 16 (V <= 2) or 8 rows per stage.
-template <int V, bool VALUED, bool MAXR, bool FUSE>
+template <int V, bool VALUED, bool MAXR, bool FUSE, bool SCALE>
 cudaError_t launch_ring1(const Args &a)
 {
     constexpr int G = V <= 2 ? 16 : 8;  // 4-8 KB of ring per warp either way
-    return launch<WalkerRing<V, VALUED, G, 2, 0, true, false, MAXR, FUSE, false, 1>, V, false, 24>(a);
+    return launch<WalkerRing<V, VALUED, G, 2, 0, true, false, MAXR, FUSE, false, 1, SCALE>, V, false, 24>(a);
 }
-template <bool VALUED, bool MAXR, bool FUSE>
+template <bool VALUED, bool MAXR, bool FUSE, bool SCALE = FUSE>
 cudaError_t dispatch_ring1(int V, const Args &a)
 {
     switch (V) {
-        case 1: return launch_ring1<1, VALUED, MAXR, FUSE>(a);
-        case 2: return launch_ring1<2, VALUED, MAXR, FUSE>(a);
-        case 3: return launch_ring1<3, VALUED, MAXR, FUSE>(a);
-        default: return launch_ring1<4, VALUED, MAXR, FUSE>(a);
+        case 1: return launch_ring1<1, VALUED, MAXR, FUSE, SCALE>(a);
+        case 2: return launch_ring1<2, VALUED, MAXR, FUSE, SCALE>(a);
+        case 3: return launch_ring1<3, VALUED, MAXR, FUSE, SCALE>(a);
+        default: return launch_ring1<4, VALUED, MAXR, FUSE, SCALE>(a);
     }
 }
 
@@ -1901,7 +1911,7 @@ cudaError_t dispatch_reg4(int V, const Args &a)
 }
 
 // ---- the families, one translation unit each ---------------------------------------------------------------------------
-// mode: 0 sum, 1 max, 2 fused sum (scales / bias)
+// mode: 0 sum, 1 max, 2 fused sum with a gathered-row scale (col_scale), 3 fused sum without one (row scale / bias only)
 cudaError_t run_ring_valued(int mode, bool peer, bool hint, int V, bool masked, const Args &a);    // gespmm_spmm_ring_valued.cu
 cudaError_t run_ring_unvalued(int mode, bool peer, bool hint, int V, bool masked, const Args &a);  // gespmm_spmm_ring_unvalued.cu
 cudaError_t run_narrow(int mode, bool valued, bool rows, int K, const Args &a);                    // gespmm_spmm_narrow.cu: K <= 64, 16-byte slices

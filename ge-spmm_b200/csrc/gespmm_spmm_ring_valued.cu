@@ -8,7 +8,8 @@ cudaError_t run_ring_valued(int mode, bool peer, bool hint, int V, bool masked, 
     constexpr bool VALUED = true;
     if (peer) return dispatch_ring<VALUED, true, false>(V, a, masked);
     if (mode == 1) return dispatch_ring<VALUED, false, true>(V, a, masked);
-    if (mode == 2) return launch_ring<1, VALUED, false, false, true, false>(a, masked);
+    if (mode == 2) return launch_ring<1, VALUED, false, false, true, false, true>(a, masked);
+    if (mode == 3) return launch_ring<1, VALUED, false, false, true, false, false>(a, masked);
     if (hint) return launch_ring<1, VALUED, false, false, false, true>(a, masked);
     return dispatch_ring<VALUED, false, false>(V, a, masked);
 }

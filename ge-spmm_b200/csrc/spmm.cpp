@@ -47,7 +47,7 @@ torch::Tensor run(const torch::Tensor &rowptr, const torch::Tensor &colind, cons
     // copies of B and C when it is handed scratch memory; the caching allocator makes that free after the first call
     gespmm_opts with_ws;
     torch::Tensor ws;
-    const size_t ws_bytes = gespmm_pad_workspace_bytes(M, N, K);
+    const size_t ws_bytes = gespmm_pad_workspace_bytes(M, N, K, nnz);
     if (ws_bytes > 0) {
         if (opts) with_ws = *opts; else gespmm_opts_init(&with_ws);
         ws = torch::empty({(int64_t)ws_bytes}, B.options().dtype(torch::kUInt8));

@@ -165,15 +165,15 @@ typedef struct gespmm_opts {
     const uint32_t *hot_columns; /* experimental: device bitmap, ceil(N / 32) words, bit c set = row c of B is among
                                 the most referenced ones ("hot": always near); NULL = none           */
     void    *workspace;      /* optional device scratch, 256-byte aligned, of at least                            */
-    size_t   workspace_bytes;/* gespmm_pad_workspace_bytes(M, N, K) bytes: lets a width that is not a multiple of 4
+    size_t   workspace_bytes;/* gespmm_pad_workspace_bytes(M, N, K, nnz) bytes: lets a width that is not a multiple of 4
                                 (K > 16) run on the 16-byte-slice walkers through padded copies of B and C when the graph
                                 is dense enough for that to pay (nnz >= 4 (M + N)): ~2x the 4-byte-slice path at K = 41,
                                 47.  Same bits either way (sequential order).  Without it nothing is padded.            */
 } gespmm_opts;
 
-/* Bytes of gespmm_opts.workspace that the padded path needs for this product; 0 when it does not apply
- * (K % 4 == 0 or K <= 16). */
-size_t gespmm_pad_workspace_bytes(int64_t M, int64_t N, int64_t K);
+/* Bytes of gespmm_opts.workspace that the padded path needs for this product; 0 when the library would not pad
+ * (K % 4 == 0, K <= 16, or a graph of fewer than 4 nonzeros per row of B and C: nnz < 4 (M + N)). */
+size_t gespmm_pad_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t nnz);
 
 void gespmm_opts_init(gespmm_opts *opts);
 

@@ -376,8 +376,9 @@ def test_widths_that_are_not_multiples_of_4_padded_and_unpadded(spmm, dev, oracl
     torch.cuda.synchronize()
     assert np.array_equal(C0.cpu().numpy()[short], want[short])
     # with a workspace, sequential flag: bit-identical again; default: within tolerance
-    need = capi.pad_workspace_bytes(M, N, K)
-    assert need >= 4 * (M + N) * ((K + 3) // 4 * 4) and capi.pad_workspace_bytes(M, N, K + (4 - K % 4)) == 0
+    need = capi.pad_workspace_bytes(M, N, K, nnz)
+    assert need >= 4 * (M + N) * ((K + 3) // 4 * 4) and capi.pad_workspace_bytes(M, N, K + (4 - K % 4), nnz) == 0
+    assert capi.pad_workspace_bytes(M, N, K, 4 * (M + N) - 1) == 0   # too sparse for the padding to pay: nothing to allocate
     ws = torch.empty(need, dtype=torch.uint8, device=dev)
     for seq in (True, False):
         C1 = torch.full((M, K), float("nan"), device=dev)
@@ -389,7 +390,7 @@ def test_widths_that_are_not_multiples_of_4_padded_and_unpadded(spmm, dev, oracl
         _check_with(oracle, rowptr, colind, vf, Bf, C1, True)
     # a graph too sparse for the padding to pay takes the 4-byte-slice walker even with a workspace: same bits
     rp_s, ci_s = _rand_csr(rng, 20000, N, 30000, empty_frac=0.3)
-    need_s = capi.pad_workspace_bytes(20000, N, K)
+    need_s = capi.pad_workspace_bytes(20000, N, K, 10**9)
     ws_s = torch.empty(need_s, dtype=torch.uint8, device=dev)
     Csp = torch.full((20000, K), float("nan"), device=dev)
     rps, cis = torch.as_tensor(rp_s, device=dev), torch.as_tensor(ci_s, device=dev)
