@@ -893,6 +893,34 @@ def test_gcnconv_matches_dense(dev, pkg):
     assert x.grad is not None and conv.weight.grad is not None and torch.isfinite(x.grad).all()
 
 
+@pytest.mark.parametrize("per_row,K", [(4, 32), (4, 128), (60, 32), (60, 128), (300, 64), (300, 128), (300, 47)])
+def test_fused_function_routes_give_the_unfused_bits(dev, pkg, per_row, K):
+    """FusedSPMMFunction scales the gathered rows inside the kernel on sparse graphs and in a pass of its own on dense ones
+    (op._fuse_gather_scale); the row scale and the bias are always inside.  Whatever the route, forward and backward carry
+    the bits of x * cs -> SPMMFunction -> * rs -> + bias (op.py:142-147)."""
+    from gespmm_b200 import graphs
+    from gespmm_b200.op import FusedSPMMFunction, SPMMFunction, _fuse_gather_scale
+    N = 3000
+    rp, ci = graphs.social_like(N, N * per_row, seed=per_row + K, device=dev)
+    assert _fuse_gather_scale(ci.numel(), N, K) == (per_row < 16 or (K > 64 and per_row < 128))
+    g = torch.Generator(device=dev).manual_seed(K)
+    rs = (torch.rand(N, 1, generator=g, device=dev) + 0.5)
+    cs = (torch.rand(N, 1, generator=g, device=dev) + 0.5)
+    for valued in (False, True):
+        ew = (torch.rand(ci.numel(), generator=g, device=dev) + 0.5) if valued else None
+        x1 = torch.randn(N, K, generator=g, device=dev).requires_grad_(True)
+        x2 = x1.detach().clone().requires_grad_(True)
+        b1 = torch.randn(K, generator=g, device=dev).requires_grad_(True)
+        b2 = b1.detach().clone().requires_grad_(True)
+        y1 = SPMMFunction.apply(rp, ci, rp, ci, x1 * cs, ew, ew) * rs + b1          # symmetric graph: CSC == CSR
+        y2 = FusedSPMMFunction.apply(rp, ci, rp, ci, x2, rs, cs, b2, ew, ew)
+        assert torch.equal(y1, y2)
+        w = torch.randn(N, K, generator=g, device=dev)
+        y1.backward(w); y2.backward(w)
+        assert torch.equal(x1.grad, x2.grad)
+        assert torch.allclose(b1.grad, b2.grad, rtol=1e-5, atol=1e-4)
+
+
 def test_gcnconv_fused_norm_and_training_loop(dev, pkg, golden_csr, tmp_path):
     """fuse_norm runs both degree normalisations and the bias add inside the kernel (gespmm_opts.row_scale / col_scale /
     bias): the layer's output and its gradients carry the BITS of the unfused layer (op.py:142-147), valued and unvalued;
