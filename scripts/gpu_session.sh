@@ -1,7 +1,9 @@
 #!/bin/bash
 # One bounded GPU session (run through gpurun from the repo root): every step under its own timeout, most
 # important first, everything into gpurun_out/.  Usage: bash scripts/gpu_session.sh [steps...]
-#   steps: subwarp sweep ksweep cli opreddit suite seq seqsuite oddk rows auto64 bench smoke sanitize launches ncu128 ncu   (default: all, in that order)
+#   steps (round 1): subwarp sweep ksweep cli opreddit suite seq seqsuite oddk rows auto64 bench smoke sanitize launches ncu128 ncu
+#   steps (round 2): uniform regreddit newtests l2sweep bulksweep l2ncu sanitize_bulk sanitize_rg sanitize_odd probel2 ncurg hotsweep
+#                    gcnlayer benchdrv multi (multi: under gpurun --gpus N -- NCCL test, bench.py at N GPUs with its R-MAT record)
 cd "$(dirname "$0")/.." || exit 1
 O=gpurun_out
 mkdir -p $O
