@@ -121,10 +121,11 @@ bool use_subwarp(int64_t K, int walker)
 cudaError_t dispatch_all(bool valued, int mode, bool vec4, bool peer, int walker, bool hint, int V, bool masked, int K, const Args &a)
 {
     if (!vec4 && K <= kRowGroupMaxK && walker != GESPMM_WALKER_REGISTER) {
-        // tiny rows of any width: lane groups on 4-byte slices.  Sequential order (GESPMM_WALKER_ROWS /
-        // GESPMM_FLAG_SEQUENTIAL): every group sums its own row (row-group kernel); default: the groups share a
-        // row's nonzeros (sub-warp walker, re-associated like its 16-byte form).
-        return run_lanegroup(mode, valued, walker == GESPMM_WALKER_ROWS || walker == GESPMM_WALKER_RING, K, a);
+        // tiny rows of any width: lane groups on 4-byte slices.  Default (and GESPMM_WALKER_SUBWARP): the groups share a
+        // row's nonzeros (sub-warp walker, re-associated like its 16-byte form); any other request -- GESPMM_FLAG_SEQUENTIAL,
+        // or a walker that sums in CSR order at the widths it was made for -- gets the sequential order: every group sums
+        // its own row (row-group kernel).  sequential_for() below says the same.
+        return run_lanegroup(mode, valued, !(walker == GESPMM_WALKER_AUTO || walker == GESPMM_WALKER_SUBWARP), K, a);
     }
     if (!vec4) return run_scalar(mode, valued, walker == GESPMM_WALKER_REGISTER, V, a);
     auto ring = valued ? run_ring_valued : run_ring_unvalued;

@@ -149,6 +149,8 @@ PY
       note "sanitize_odd done" ;;
     gcnlayer) # fused vs unfused aggregation half of a GCN layer, and the training loop per epoch
       timeout 600 python scripts/gcn_layer_bench.py > $O/gcn_layer.txt 2> $O/gcn_layer.err; note "gcnlayer rc=$?" ;;
+    fuzz)     # randomised differential test of the C ABI against the oracle
+      timeout 900 python scripts/fuzz_gpu.py --cases ${FUZZ_CASES:-800} > $O/fuzz.txt 2>&1; note "fuzz rc=$?" ;;
     rows)     # sub-warp (2) vs row-parallel (4) narrow walkers on every shape
       timeout 600 python scripts/sweep_narrow.py --variants 2,4 --tasks 0 > $O/sweep_v24.txt 2> $O/sweep_v24.err; note "rows rc=$?" ;;
     auto64)   # the SpMM suite with the sub-warp walker chosen automatically for K <= 64
