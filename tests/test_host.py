@@ -77,6 +77,22 @@ def test_argument_validation_without_a_device(pkg):
     assert f(4, 4, 8, 2**31, one, one, None, one, 8, one, 8, None) == capi.ERR_TOO_LARGE
     assert f(0, 4, 8, 0, None, None, None, None, 8, None, 8, None) == capi.OK                 # nothing to do
     assert f(4, 4, 0, 0, one, None, None, None, 0, None, 0, None) == capi.OK
+    assert f(4, 4, 8, 2**31 - 65535, one, one, None, one, 8, one, 8, None) == capi.ERR_TOO_LARGE   # 64 K of int32 headroom for position sums
+    # the per-call options: an opts struct of another ABI version is refused; fused vectors do not combine with sharded B
+    g = L.gespmm_csr_spmm_f32_ex
+    o = capi.opts(sequential=True)
+    assert g(-1, 1, 1, 0, one, one, None, one, 1, one, 1, ctypes.byref(o), None) == capi.ERR_INVALID_ARG
+    assert g(0, 4, 8, 0, None, None, None, None, 8, None, 8, ctypes.byref(o), None) == capi.OK
+    o.struct_size = 12
+    assert g(4, 4, 8, 3, one, one, None, one, 8, one, 8, ctypes.byref(o), None) == capi.ERR_INVALID_ARG
+    assert capi.pad_workspace_bytes(100, 200, 41, 10**6) >= 4 * 300 * 44 and capi.pad_workspace_bytes(100, 200, 41, 10**6) % 256 == 0
+    assert capi.pad_workspace_bytes(100, 200, 44, 10**6) == 0 and capi.pad_workspace_bytes(100, 200, 7, 10**6) == 0
+    assert capi.pad_workspace_bytes(100, 200, 41, 4 * 300 - 1) == 0                                   # too sparse to pay
+    out = ctypes.c_int32(-5)
+    assert L.gespmm_max_row_nnz(-1, one, ctypes.byref(out), None) == capi.ERR_INVALID_ARG
+    assert L.gespmm_max_row_nnz(0, None, ctypes.byref(out), None) == capi.OK and out.value == 0
+    assert L.gespmm_max_row_nnz(4, one, None, None) == capi.ERR_INVALID_ARG
+    L.gespmm_thread_cleanup()   # nothing to release: a no-op, not a crash
     assert L.gespmm_csr2csc_f32(4, 4, 3, one, one, None, one, one, None, one, 8, None) == capi.ERR_WORKSPACE
     assert L.gespmm_csr2csc_f32(4, 4, 3, one, one, one, one, one, None, one, 1 << 30, None) == capi.ERR_INVALID_ARG
     assert L.gespmm_csr2csc_workspace_bytes(10, 10, 1000) >= 5 * 4 * 1000
