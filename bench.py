@@ -763,6 +763,10 @@ def main():
                     "bitwise_equal_to_ours": bool(torch.equal(Crl, Cl)),
                     "bitwise_equal_on_rows_up_to_GESPMM_LONG_ROW": bool(torch.equal(Crl[short], Cl[short])),
                     "max_abs_diff": float((Crl - Cl).abs().max())}
+                # the reference's own kernel on the same inputs is part of the parity verdict of this run
+                if spmm.row_sum_is_sequential(K, 2):   # (widths whose default walker re-associates are held to 1e-4, not to bits)
+                    parity["reference_kernel_bitwise_on_rows_up_to_GESPMM_LONG_ROW"] = out["reference_kernel_same_gpu"]["bitwise_equal_on_rows_up_to_GESPMM_LONG_ROW"]
+                    parity["ok"] = parity["ok"] and parity["reference_kernel_bitwise_on_rows_up_to_GESPMM_LONG_ROW"]
                 del Cr, ones, Cl
             except Exception as e:
                 out["reference_kernel_same_gpu"] = {"error": repr(e)}
