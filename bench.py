@@ -162,7 +162,7 @@ def physical_gpu_index(local_index):
 
 LONG_ROW = 4096               # GESPMM_LONG_ROW (include/gespmm.h)
 L2_GATHER_PEAK_GBS = 17900.0  # bin/membench on this pool: random 512-byte rows out of an L2-resident table (profiles/r01_membench.txt)
-L2_RESIDENT_BYTES = 100 * 2**20  # the table size up to which membench holds that rate (126 MB L2)
+L2_RESIDENT_BYTES = 126 * 2**20  # the L2: membench holds 17.5-17.9 TB/s up to a 100 MB table and 15.1 TB/s at 134 MB
 N_BATCHES = 5
 
 
