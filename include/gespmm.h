@@ -131,10 +131,13 @@ int gespmm_csr_spmm_max_f32(int64_t M, int64_t N, int64_t K, int64_t nnz,
  */
 #define GESPMM_FLAG_SEQUENTIAL  0x1u  /* sum every row of at most GESPMM_LONG_ROW nonzeros in strictly sequential CSR
                                          order for every K (bit-identical to the reference kernels); without it the
-                                         faster re-associating sub-warp walker is used for K <= 64 */
+                                         faster re-associating sub-warp walker is used for K <= 64 (K % 4 == 0) and
+                                         for any K <= 16 */
 #define GESPMM_FLAG_NO_OVERLAP  0x2u  /* run the long-row kernel on `stream` itself, not on the helper stream */
 
-/* values of gespmm_opts.walker (tuning / comparisons; 0 = automatic) */
+/* values of gespmm_opts.walker (tuning / comparisons; 0 = automatic).  A walker asked for at a width it does not cover
+ * falls back to the walker of that width with the same summation order (e.g. any request but AUTO / SUBWARP at
+ * K <= 16 on 4-byte slices runs the sequential row-group kernel). */
 #define GESPMM_WALKER_AUTO      0
 #define GESPMM_WALKER_RING      1     /* cp.async gather ring, one nonzero per warp-wide copy, sequential order */
 #define GESPMM_WALKER_REGISTER  2     /* register-staged gathers (no shared memory), sequential order           */
@@ -159,7 +162,9 @@ typedef struct gespmm_opts {
     int32_t  task_keys;      /* keys (rows + nonzeros) per task of the main kernel, multiple of 32 in [32, 1024]  */
     int32_t  long_row;       /* long-row threshold override, [512, 2^20]                                         */
     int32_t  panel_v;        /* 128-column blocks per pass (1..4)                                                */
-    int32_t  l2_policy;      /* experimental: L2 eviction-priority steering of the B gathers, see DESIGN.md 3.5  */
+    int32_t  l2_policy;      /* experimental: near + 4 far + 16 store, each 0 normal / 1 evict_first / 2 evict_last /
+                                3 unchanged: L2 eviction priorities of the C stores (any walker) and of the gathered
+                                rows (GESPMM_WALKER_BULK only); same bits whatever the value.  DESIGN.md 3.6b     */
     int32_t  l2_window_rows; /* experimental: |col - row| up to which a gathered row counts as "near" (0 = default
                                 131072, negative = no band at all)                                             */
     const uint32_t *hot_columns; /* experimental: device bitmap, ceil(N / 32) words, bit c set = row c of B is among
